@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: Gvoxels/s of voxelize + CSG + JFA signed-distance field at 1024^3 on the 1 348 128-face
+subdivided bunny (∪ bimba), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 1024] [--faces 1348128]
+
+A step = one pass of the hot path over the workload: voxelize both meshes, fold them with CSG union, extract
+seeds, run all JFA passes, write the signed squared distance.  `value` is device-resident throughput (meshes
+already in HBM, CUDA-event timed on the launching stream); `e2e` goes through the reference-facing C-ABI call
+vpb_pipeline_host with pinned HOST buffers, H2D and D2H inside the timed region.  `--impl reference` times the
+reference's own CPU implementation (oracle/_ref, all host threads) on a bounded sample of the same workload.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Gvoxels/s voxelize+CSG+JFA SDF"
+UNIT = "Gvoxels/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_workload(n, faces):
+    from cuda_mesh_voxelization_b200 import meshgen, shared_frame
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    bunny = meshgen.bunny_with_faces(z["bunny_v"], z["bunny_t"], faces)
+    bimba = (z["bimba_v"], z["bimba_t"])
+    meshes = [bunny, bimba]
+    origin, vs = shared_frame([m[0] for m in meshes], n)
+    return meshes, origin, vs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per JFA-pass launch from the committed ncu capture summary, if any (profiles/*.json)."""
+    p = os.path.join(ROOT, "profiles", "jfa_pass_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+
+def cpu_pipeline(lib, kind, meshes, n, origin_vs=None):
+    """One pass of the reference CPU path (-t 3 flavour: sequential voxelization — the only CPU voxelizer the CLI
+    ever calls, apps/cli/main.cpp:99-103 — then OpenMP CSG and JFA with every host thread)."""
+    if origin_vs is None:
+        origin, vs = lib.frame(np.concatenate([m[0] for m in meshes]), n)
+    else:
+        origin, vs = origin_vs
+    t0 = time.perf_counter()
+    grids = [lib.voxelize(*m, n, vs, origin) for m in meshes]
+    if kind == "reference":
+        acc = lib.csg(grids[0], grids[1], n, 1, openmp=True)
+        lib.jfa(acc, n, vs, origin, openmp=True)
+    else:
+        acc = lib.csg(grids[0], grids[1], n, 1)
+        lib.jfa(acc, n, vs, origin)
+    return time.perf_counter() - t0
+
+
+def cpu_arm():
+    from checkers import Oracle, Reference
+    if Reference.available():
+        return Reference(), "reference"
+    return Oracle(), "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind = cpu_arm()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    n_s = args.ref_n
+    meshes, _, _ = load_workload(n_s, args.faces)
+    for _ in range(args.warmup):
+        cpu_pipeline(lib, kind, meshes, n_s)
+    t = [cpu_pipeline(lib, kind, meshes, n_s) for _ in range(args.steps)]
+    total = sum(t)
+    value = n_s ** 3 * args.steps / total / 1e9
+    sample = (f"{n_s}^3 grid per step (the workload's meshes and stages at 1/{(args.n // n_s) ** 3} of its voxels): "
+              f"sequential voxelization + OpenMP CSG + OpenMP JFA, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cpu_sample_n": n_s},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"bunny subdivided to {args.faces} faces ∪ bimba (46220 faces), solid voxelization + CSG union + JFA SDF "
+            f"at {args.n}^3")
+
+
+# ------------------------------------------------------------------------------------------ our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh, DevicePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n = args.n
+    meshes, origin, vs = load_workload(n, args.faces)
+    dev = f"cuda:{local}"
+    capi.init(local)
+
+    if world > 1:
+        from cuda_mesh_voxelization_b200.multi import SlabPipeline
+        pipe = SlabPipeline(n, vs, origin, rank, world, device=dev)
+    else:
+        pipe = DevicePipeline(n, vs, origin, device=dev, max_tris=max(m[1].shape[0] for m in meshes))
+    dmeshes = [DeviceMesh(v, t, dev) for v, t in meshes]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pipe.run(dmeshes, op=capi.OP_UNION, sdf=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.kernel_launches()
+    pipe.pass_events.clear()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run(dmeshes, op=capi.OP_UNION, sdf=True, record_passes=True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = capi.kernel_launches() - launches0
+
+    # dominant kernel: the JFA flood pass (all but the cheap first passes run ~the same code at full density)
+    pass_ms = {}
+    for k, a, b in pipe.pass_events:
+        pass_ms.setdefault(k, []).append(a.elapsed_time(b))
+    slab_voxels = pipe.slab_voxels if world > 1 else n ** 3
+    pass_avg = {k: float(np.mean(v)) for k, v in pass_ms.items()}
+    mean_pass_ms = float(np.mean([np.mean(v) for v in pass_ms.values()])) if pass_ms else None
+    peak, peak_src = hbm_peak()
+    alg_bytes = 8.0 * slab_voxels  # 4 B state read + 4 B state (or sdf) write per voxel per pass
+    achieved = alg_bytes / (mean_pass_ms * 1e-3) / 1e9 if mean_pass_ms else None
+    traffic = ncu_traffic()
+
+    # ---- end to end through the reference-facing C-ABI call, host buffers, copies inside the timed region
+    e2e = None
+    if world == 1:
+        pv = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v, _ in meshes]
+        pt = [torch.from_numpy(np.ascontiguousarray(t).view(np.int32)).pin_memory() for _, t in meshes]
+        host_meshes = [(a.numpy(), b.numpy().view(np.uint32)) for a, b in zip(pv, pt)]
+        sdf_host = torch.empty(n ** 3, dtype=torch.float32).pin_memory()
+        words_host = torch.empty(capi.n_words(n), dtype=torch.int32).pin_memory()
+        del pipe
+        torch.cuda.empty_cache()
+        kw = dict(op=capi.OP_UNION, sdf_out=sdf_host.numpy(), words_out=words_host.numpy().view(np.uint32))
+        for _ in range(max(1, min(args.warmup, 2))):
+            capi.pipeline_host(host_meshes, n, vs, origin, **kw)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            capi.pipeline_host(host_meshes, n, vs, origin, **kw)
+        dt = time.perf_counter() - t0
+        h2d = sum(v.nbytes + t.nbytes for v, t in host_meshes)
+        d2h = n ** 3 * 4 + capi.n_words(n) * 4
+        e2e = {"value": n ** 3 * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / args.steps * 1e3, "stages_ms": capi.last_timing(),
+               "api": "vpb_pipeline_host (pinned host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it: the reference's own CPU path on a bounded sample (N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        lib, kind = cpu_arm()
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        n_s = args.ref_n
+        ms_, _, _ = load_workload(n_s, args.faces)
+        dt = cpu_pipeline(lib, kind, ms_, n_s)
+        cpu = {"value": n_s ** 3 / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"one step at {n_s}^3 (same meshes and stages, 1/{(n // n_s) ** 3} of the voxels): sequential "
+                         f"voxelization + OpenMP CSG + OpenMP JFA, {dt:.2f} s"}
+
+    value = n ** 3 * args.steps / (ms_total * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": "union",
+                   "l2": "per-step working set (2 x 4.3 GB seed state + 4.3 GB sdf) >> 126 MB L2, no flush needed",
+                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass"},
+        "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the log2(N) passes of a step)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
+                     "ms_per_launch": mean_pass_ms, "ms_per_pass_by_k": {str(k): v for k, v in sorted(pass_avg.items(), reverse=True)}},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--faces", type=int, default=1348128)
+    ap.add_argument("--ref-n", type=int, default=128, help="grid side of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,364 @@
+// C ABI of libvpb200 (include/vpb200.h): context, pooled buffers, host-buffer stage calls, pipeline.
+//
+// Replaces the reference's per-call CudaPtr<T> malloc/copy/free pattern (vplib/src/cuda_ptr.h:14-93,
+// e.g. vox/naive.cu:91-121, jfa/tiled.cu:250-336) with one stream, grow-only device buffers that survive
+// between calls, and stage-to-stage device residency inside vpb_pipeline_host.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace vpb {
+
+namespace {
+
+thread_local char g_err[512] = "";
+uint64_t g_launches = 0;
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return VPB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        // round up so that repeated slightly-growing requests do not reallocate
+        size_t want = ((bytes + (1u << 20) - 1) >> 20) << 20;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return VPB_ERR_NOMEM;
+        }
+        cap = want;
+        return VPB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float timing[3] = {0, 0, 0};
+    Buf verts, tris, grid_a, grid_b, scratch, state_a, state_b, sdf, seeds;
+};
+Context g_ctx;
+
+#define VPB_TRY(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != VPB_OK) return _rc; \
+    } while (0)
+
+int require_ready() {
+    if (!g_ctx.ready) {
+        set_error("vpb_init has not been called (or failed)");
+        return VPB_ERR_STATE;
+    }
+    return VPB_OK;
+}
+
+Frame make_frame(uint32_t n, float vs, const float origin[3]) { return Frame{origin[0], origin[1], origin[2], vs, n}; }
+
+// Runs seed extraction + all passes + signed output on one GPU.
+int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st) {
+    const uint32_t n = f.n;
+    VPB_TRY(jfa_seed_launch(words, n, 0, n, sa, st));
+    const uint64_t plane = (uint64_t)n * n;
+    uint32_t* in = sa;
+    uint32_t* out = sb;
+    if (n / 2 == 0) return jfa_finalize_launch(in, f, 0, n, words, sdf, seeds, st);
+    for (uint32_t k = n / 2; k >= 1; k /= 2) {
+        const bool last = (k == 1);
+        VPB_TRY(jfa_pass_launch(in - k * plane, in, in + k * plane, out, f, 0, n, k, words, last ? sdf : nullptr,
+                                last ? seeds : nullptr, st));
+        uint32_t* t = in; in = out; out = t;
+    }
+    return VPB_OK;
+}
+
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+void count_launch(unsigned n) { g_launches += n; }
+int num_sms() { return g_ctx.sms; }
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+int vpb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int vpb_init(int device) {
+    if (g_ctx.ready && g_ctx.device == device) return VPB_OK;
+    if (g_ctx.ready) vpb_shutdown();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); vpb200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return VPB_ERR_CUDA;
+    }
+    VPB_REQUIRE(device >= 0 && device < count, "vpb_init: device %d out of range (count %d)", device, count);
+    VPB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return VPB_ERR_CUDA;
+    }
+    g_ctx.sms = prop.multiProcessorCount;
+    g_ctx.device = device;
+    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    for (auto& ev : g_ctx.ev) VPB_CUDA(cudaEventCreate(&ev));
+    g_ctx.ready = true;
+    g_launches = 0;
+    return VPB_OK;
+}
+
+void vpb_shutdown(void) {
+    if (!g_ctx.ready) return;
+    cudaSetDevice(g_ctx.device);
+    cudaStreamSynchronize(g_ctx.stream);
+    for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.scratch, &g_ctx.state_a,
+                   &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds})
+        b->release();
+    for (auto& ev : g_ctx.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+    g_ctx.ready = false;
+}
+
+const char* vpb_last_error(void) { return g_err; }
+uint64_t vpb_kernel_launches(void) { return g_launches; }
+
+int vpb_last_timing(float out[3]) {
+    VPB_REQUIRE(out, "vpb_last_timing: null");
+    memcpy(out, g_ctx.timing, sizeof g_ctx.timing);
+    return VPB_OK;
+}
+
+// ---------------------------------------------------------------------------------- device-pointer calls
+
+size_t vpb_voxelize_scratch_bytes(uint32_t n, uint64_t n_tris, uint32_t z0, uint32_t z1) {
+    return vox_scratch_bytes(n, n_tris, z0, z1);
+}
+
+int vpb_voxelize_dev(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, uint32_t n, float vs,
+                     const float origin[3], uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin, "voxelize: null origin");
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
+    return vox_launch(verts, n_verts, tris, n_tris, make_frame(n, vs, origin), z0, z1, words_slab, scratch, scratch_bytes, st);
+}
+
+int vpb_csg_dev(uint32_t* a, const uint32_t* b, uint64_t n_words, int op, void* stream) {
+    VPB_TRY(require_ready());
+    return csg_launch(a, b, n_words, op, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell, void* stream) {
+    VPB_TRY(require_ready());
+    return shell_launch(words, n, shell, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1) {
+    if (z1 <= z0 || z1 > n) return 0;
+    return (size_t)n * n * (z1 - z0) * sizeof(uint32_t);
+}
+
+int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, void* stream) {
+    VPB_TRY(require_ready());
+    return jfa_seed_launch(words_full, n, z0, z1, state, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, uint32_t n,
+                     uint32_t z0, uint32_t z1, uint32_t k, float vs, const float origin[3], const uint32_t* words_full,
+                     float* sdf, uint32_t* seeds, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin, "jfa_pass: null origin");
+    return jfa_pass_launch(below, mid, above, dst, make_frame(n, vs, origin), z0, z1, k, words_full, sdf, seeds,
+                           stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_jfa_finalize_dev(const uint32_t* state, uint32_t n, uint32_t z0, uint32_t z1, float vs, const float origin[3],
+                         const uint32_t* words_full, float* sdf, uint32_t* seeds, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin, "jfa_finalize: null origin");
+    return jfa_finalize_launch(state, make_frame(n, vs, origin), z0, z1, words_full, sdf, seeds,
+                               stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_jfa_dev(const uint32_t* words, uint32_t n, float vs, const float origin[3], uint32_t* sa, uint32_t* sb,
+                float* sdf, uint32_t* seeds, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(words && sa && sb && sdf && origin, "jfa: null buffer");
+    VPB_REQUIRE(n > 0 && n <= 1024, "jfa: unsupported n=%u (32-bit state needs N <= 1024)", n);
+    return jfa_run(words, make_frame(n, vs, origin), sa, sb, sdf, seeds, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+// ---------------------------------------------------------------------------------- host-buffer calls
+
+static int finish_timing() {
+    cudaStream_t st = g_ctx.stream;
+    VPB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0;
+        VPB_CUDA(cudaEventElapsedTime(&ms, g_ctx.ev[i], g_ctx.ev[i + 1]));
+        g_ctx.timing[i] = ms;
+    }
+    return VPB_OK;
+}
+
+static int upload_mesh(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, cudaStream_t st) {
+    VPB_TRY(g_ctx.verts.reserve(n_verts * 12 + 16));
+    VPB_TRY(g_ctx.tris.reserve(n_tris * 12 + 16));
+    if (n_verts) VPB_CUDA(cudaMemcpyAsync(g_ctx.verts.p, verts, n_verts * 12, cudaMemcpyHostToDevice, st));
+    if (n_tris) VPB_CUDA(cudaMemcpyAsync(g_ctx.tris.p, tris, n_tris * 12, cudaMemcpyHostToDevice, st));
+    return VPB_OK;
+}
+
+int vpb_voxelize_host(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, uint32_t n, float vs,
+                      const float origin[3], int mode, uint32_t* words_out) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(words_out && origin && n > 0, "voxelize: bad argument");
+    VPB_REQUIRE(mode == VPB_MODE_SOLID || mode == VPB_MODE_SURFACE, "voxelize: bad mode %d", mode);
+    VPB_REQUIRE(n_tris == 0 || (verts && tris), "voxelize: null mesh");
+    cudaStream_t st = g_ctx.stream;
+    const uint64_t nw = grid_words(n);
+    const size_t sb = vox_scratch_bytes(n, n_tris, 0, n);
+    VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
+    VPB_TRY(g_ctx.scratch.reserve(sb));
+    if (mode == VPB_MODE_SURFACE) VPB_TRY(g_ctx.grid_b.reserve(nw * 4 + 16));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
+    VPB_TRY(upload_mesh(verts, n_verts, tris, n_tris, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
+    VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts, g_ctx.tris.as<uint32_t>(), n_tris, make_frame(n, vs, origin), 0, n,
+                       g_ctx.grid_a.as<uint32_t>(), g_ctx.scratch.p, g_ctx.scratch.cap, st));
+    const uint32_t* result = g_ctx.grid_a.as<uint32_t>();
+    if (mode == VPB_MODE_SURFACE) {
+        VPB_TRY(shell_launch(g_ctx.grid_a.as<uint32_t>(), n, g_ctx.grid_b.as<uint32_t>(), st));
+        result = g_ctx.grid_b.as<uint32_t>();
+    }
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+    VPB_CUDA(cudaMemcpyAsync(words_out, result, nw * 4, cudaMemcpyDeviceToHost, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
+    return finish_timing();
+}
+
+int vpb_csg_host(uint32_t* a, const uint32_t* b, uint32_t n, int op) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(a && b && n > 0, "csg: bad argument");
+    VPB_REQUIRE(op >= VPB_OP_UNION && op <= VPB_OP_DIFFERENCE, "csg: bad op %d", op);
+    cudaStream_t st = g_ctx.stream;
+    const uint64_t nw = grid_words(n);
+    VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
+    VPB_TRY(g_ctx.grid_b.reserve(nw * 4 + 16));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
+    VPB_CUDA(cudaMemcpyAsync(g_ctx.grid_a.p, a, nw * 4, cudaMemcpyHostToDevice, st));
+    VPB_CUDA(cudaMemcpyAsync(g_ctx.grid_b.p, b, nw * 4, cudaMemcpyHostToDevice, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
+    VPB_TRY(csg_launch(g_ctx.grid_a.as<uint32_t>(), g_ctx.grid_b.as<uint32_t>(), nw, op, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+    VPB_CUDA(cudaMemcpyAsync(a, g_ctx.grid_a.p, nw * 4, cudaMemcpyDeviceToHost, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
+    return finish_timing();
+}
+
+static int reserve_jfa(uint32_t n, bool want_seeds) {
+    const size_t vox = (size_t)n * n * n;
+    VPB_TRY(g_ctx.state_a.reserve(vox * 4));
+    VPB_TRY(g_ctx.state_b.reserve(vox * 4));
+    VPB_TRY(g_ctx.sdf.reserve(vox * 4));
+    if (want_seeds) VPB_TRY(g_ctx.seeds.reserve(vox * 4));
+    return VPB_OK;
+}
+
+int vpb_jfa_host(const uint32_t* words, uint32_t n, float vs, const float origin[3], float* sdf_out, uint32_t* seeds_out) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(words && sdf_out && origin, "jfa: null buffer");
+    VPB_REQUIRE(n > 0 && n <= 1024, "jfa: unsupported n=%u (32-bit state needs N <= 1024)", n);
+    cudaStream_t st = g_ctx.stream;
+    const uint64_t nw = grid_words(n);
+    const size_t vox = (size_t)n * n * n;
+    VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
+    VPB_TRY(reserve_jfa(n, seeds_out != nullptr));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
+    VPB_CUDA(cudaMemcpyAsync(g_ctx.grid_a.p, words, nw * 4, cudaMemcpyHostToDevice, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
+    VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), make_frame(n, vs, origin), g_ctx.state_a.as<uint32_t>(),
+                    g_ctx.state_b.as<uint32_t>(), g_ctx.sdf.as<float>(), seeds_out ? g_ctx.seeds.as<uint32_t>() : nullptr, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+    VPB_CUDA(cudaMemcpyAsync(sdf_out, g_ctx.sdf.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    if (seeds_out) VPB_CUDA(cudaMemcpyAsync(seeds_out, g_ctx.seeds.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
+    return finish_timing();
+}
+
+int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n_verts, const uint32_t* const* tris,
+                      const uint64_t* n_tris, uint32_t n, float vs, const float origin[3], int op, uint32_t* words_out,
+                      float* sdf_out) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(n_meshes >= 1 && verts && n_verts && tris && n_tris && origin && n > 0, "pipeline: bad argument");
+    VPB_REQUIRE(op >= VPB_OP_VOID && op <= VPB_OP_DIFFERENCE, "pipeline: bad op %d", op);
+    VPB_REQUIRE(!sdf_out || n <= 1024, "pipeline: sdf needs N <= 1024 (32-bit state)");
+    cudaStream_t st = g_ctx.stream;
+    const uint64_t nw = grid_words(n);
+    const size_t vox = (size_t)n * n * n;
+    const Frame f = make_frame(n, vs, origin);
+    uint64_t max_tris = 0;
+    for (int i = 0; i < n_meshes; ++i) max_tris = n_tris[i] > max_tris ? n_tris[i] : max_tris;
+    VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
+    if (n_meshes > 1) VPB_TRY(g_ctx.grid_b.reserve(nw * 4 + 16));
+    VPB_TRY(g_ctx.scratch.reserve(vox_scratch_bytes(n, max_tris, 0, n)));
+    if (sdf_out) VPB_TRY(reserve_jfa(n, false));
+    // H2D of mesh i and its kernels are interleaved on one stream; ev[0..1] bracket the first upload only,
+    // the rest is accounted to "kernels" (there is a single timeline).
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
+    for (int i = 0; i < n_meshes; ++i) {
+        VPB_TRY(upload_mesh(verts[i], n_verts[i], tris[i], n_tris[i], st));
+        if (i == 0) VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
+        uint32_t* target = i == 0 ? g_ctx.grid_a.as<uint32_t>() : g_ctx.grid_b.as<uint32_t>();
+        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts[i], g_ctx.tris.as<uint32_t>(), n_tris[i], f, 0, n, target,
+                           g_ctx.scratch.p, g_ctx.scratch.cap, st));
+        // apps/cli/main.cpp:126-186: fold into grids[0] for i > 0 when an operator is selected
+        if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(g_ctx.grid_a.as<uint32_t>(), g_ctx.grid_b.as<uint32_t>(), nw, op, st));
+    }
+    if (sdf_out)
+        VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(),
+                        g_ctx.sdf.as<float>(), nullptr, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+    if (words_out) VPB_CUDA(cudaMemcpyAsync(words_out, g_ctx.grid_a.p, nw * 4, cudaMemcpyDeviceToHost, st));
+    if (sdf_out) VPB_CUDA(cudaMemcpyAsync(sdf_out, g_ctx.sdf.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
+    return finish_timing();
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Shared declarations of the vpb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+
+#include "../../include/vpb200.h"
+
+namespace vpb {
+
+// ---- error plumbing: kernels' host launchers return vpb_status and record a message ----------
+void set_error(const char* fmt, ...);
+void count_launch(unsigned n = 1);
+
+#define VPB_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::vpb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return VPB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define VPB_LAUNCH_CHECK()                                                                    \
+    do {                                                                                      \
+        ::vpb::count_launch();                                                                \
+        VPB_CUDA(cudaPeekAtLastError());                                                      \
+    } while (0)
+
+#define VPB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            ::vpb::set_error(__VA_ARGS__);                                                    \
+            return VPB_ERR_ARG;                                                               \
+        }                                                                                     \
+    } while (0)
+
+// Grid frame shared by every stage (vplib: VoxelsGrid::{VoxelSize,OriginX/Y/Z,VoxelsPerSide}).
+struct Frame {
+    float ox, oy, oz;
+    float vs;
+    uint32_t n;
+};
+
+static inline uint64_t words_for_bits(uint64_t bits) { return (bits + 31u) / 32u; }
+static inline uint64_t grid_words(uint32_t n) { return words_for_bits((uint64_t)n * n * n); }
+
+int num_sms();
+
+// ---- JFA state word (N <= 1024): bit0 = valid, x -> bits 2..11, y -> 12..21, z -> 22..31.
+// The fields sit where `(s >> shift) & 0xFFC` is directly the byte offset into a float table.
+// 0 = "no seed" (also what TMA / zero-fill produce outside the grid).
+__host__ __device__ __forceinline__ uint32_t jfa_pack(uint32_t x, uint32_t y, uint32_t z) {
+    return 1u | (x << 2) | (y << 12) | (z << 22);
+}
+__host__ __device__ __forceinline__ uint32_t jfa_x(uint32_t s) { return (s >> 2) & 1023u; }
+__host__ __device__ __forceinline__ uint32_t jfa_y(uint32_t s) { return (s >> 12) & 1023u; }
+__host__ __device__ __forceinline__ uint32_t jfa_z(uint32_t s) { return s >> 22; }
+// public encoding of vpb200.h: x | y<<10 | z<<20, 0xFFFFFFFF = none
+__host__ __device__ __forceinline__ uint32_t jfa_public(uint32_t s) { return s ? (s >> 2) : 0xFFFFFFFFu; }
+
+#ifdef __CUDACC__
+// ---- bit-grid helpers shared by the shell and seed kernels ----------------------------------------
+__device__ __forceinline__ bool bit_at(const uint32_t* __restrict__ words, uint64_t i) {
+    return (__ldg(words + (i >> 5)) >> (i & 31u)) & 1u;
+}
+
+// "all 27 voxels of the 3x3x3 neighbourhood are set and inside the grid", for the 32 voxels of word xw of row (y,z)
+__device__ __forceinline__ uint32_t interior_mask32(const uint32_t* __restrict__ words, uint32_t n, uint32_t R,
+                                                    uint32_t xw, uint32_t y, uint32_t z) {
+    if (y == 0 || z == 0 || y + 1 >= n || z + 1 >= n) return 0u;
+    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const uint32_t* row = words + ((uint64_t)(z + dz) * n + (y + dy)) * R;
+            const uint32_t c = __ldg(row + xw);
+            const uint32_t l = xw > 0 ? __ldg(row + xw - 1) : 0u;
+            const uint32_t r = xw + 1 < R ? __ldg(row + xw + 1) : 0u;
+            m &= c & ((c << 1) | (l >> 31)) & ((c >> 1) | (r << 31));
+        }
+    return m;
+}
+
+#endif  // __CUDACC__
+
+// ---- stage launchers (each in its own .cu) -------------------------------------------------------
+size_t vox_scratch_bytes(uint32_t n, uint64_t n_tris, uint32_t z0, uint32_t z1);
+int vox_launch(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, const Frame& f,
+               uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int csg_launch(uint32_t* a, const uint32_t* b, uint64_t n_words, int op, cudaStream_t st);
+int shell_launch(const uint32_t* words, uint32_t n, uint32_t* shell, cudaStream_t st);
+int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
+int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,
+                    uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
+                    cudaStream_t st);
+int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
+                        float* sdf, uint32_t* seeds, cudaStream_t st);
+
+}  // namespace vpb

@@ -1,0 +1,122 @@
+"""Device-resident pipeline on torch-owned memory (the metric path).
+
+torch is plumbing only: it owns the HBM buffers and the stream; every kernel is ours (libvpb200.so) and is
+launched through the device-pointer C ABI on torch's current stream, so torch.cuda.Event timing sees it.
+Nothing leaves the GPU between voxelization, CSG, seed extraction, the flood passes and the signed output —
+the reference's CUDA back-ends re-upload and re-download every stage (e.g. jfa/tiled.cu:250-336).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceMesh:
+    def __init__(self, verts: np.ndarray, tris: np.ndarray, device):
+        self.n_verts = int(verts.shape[0])
+        self.n_tris = int(tris.shape[0])
+        self.verts = torch.from_numpy(np.ascontiguousarray(verts, np.float32)).to(device)
+        # uint32 indices travel as int32 bit patterns (torch has no first-class uint32 storage ops)
+        self.tris = torch.from_numpy(np.ascontiguousarray(tris, np.uint32).view(np.int32)).to(device)
+
+    @property
+    def nbytes(self):
+        return self.n_verts * 12 + self.n_tris * 12
+
+
+class DevicePipeline:
+    """Single-GPU voxelize -> CSG fold -> JFA SDF with all buffers resident.  N <= 1024 (32-bit seed state)."""
+
+    def __init__(self, n: int, voxel_size, origin, device="cuda:0", want_seeds=False, max_tris=0):
+        self.lib = capi.load()
+        self.n = int(n)
+        self.vs = float(voxel_size)
+        self.origin = np.ascontiguousarray(origin, np.float32)
+        self.device = torch.device(device)
+        capi.init(self.device.index or 0)
+        nw = capi.n_words(self.n)
+        vox = self.n ** 3
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.grid_a = torch.empty(nw, **i32)
+        self.grid_b = torch.empty(nw, **i32)
+        self.state_a = torch.empty(vox, **i32)
+        self.state_b = torch.empty(vox, **i32)
+        self.sdf = torch.empty(vox, dtype=torch.float32, device=self.device)
+        self.seeds = torch.empty(vox, **i32) if want_seeds else None
+        self.scratch = None
+        self._reserve_scratch(max_tris)
+        self.pass_events = []  # [(k, start_event, end_event)] when record_passes=True
+
+    def _reserve_scratch(self, n_tris):
+        need = int(self.lib.vpb_voxelize_scratch_bytes(self.n, n_tris, 0, self.n))
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+
+    def _o(self):
+        return self.origin.ctypes.data_as(_f32p)
+
+    def voxelize(self, mesh: DeviceMesh, into):
+        self._reserve_scratch(mesh.n_tris)
+        capi.check(self.lib.vpb_voxelize_dev(_ptr(mesh.verts), mesh.n_verts, _ptr(mesh.tris), mesh.n_tris, self.n,
+                                             self.vs, self._o(), 0, self.n, _ptr(into), _ptr(self.scratch),
+                                             self.scratch.numel(), _stream()))
+
+    def csg(self, op):
+        capi.check(self.lib.vpb_csg_dev(_ptr(self.grid_a), _ptr(self.grid_b), self.grid_a.numel(), op, _stream()))
+
+    def jfa(self, record_passes=False):
+        n, st = self.n, _stream()
+        capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_a), n, 0, n, _ptr(self.state_a), st))
+        src, dst = self.state_a, self.state_b
+        if n // 2 == 0:
+            capi.check(self.lib.vpb_jfa_finalize_dev(_ptr(src), n, 0, n, self.vs, self._o(), _ptr(self.grid_a),
+                                                     _ptr(self.sdf), _ptr(self.seeds), st))
+            return
+        plane_bytes = n * n * 4
+        k = n // 2
+        while k >= 1:
+            last = k == 1
+            base = src.data_ptr()
+            if record_passes:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            capi.check(self.lib.vpb_jfa_pass_dev(ctypes.c_void_p(base - k * plane_bytes), ctypes.c_void_p(base),
+                                                 ctypes.c_void_p(base + k * plane_bytes), _ptr(dst), n, 0, n, k,
+                                                 self.vs, self._o(), _ptr(self.grid_a) if last else None,
+                                                 _ptr(self.sdf) if last else None,
+                                                 _ptr(self.seeds) if last else None, st))
+            if record_passes:
+                e1.record()
+                self.pass_events.append((k, e0, e1))
+            src, dst = dst, src
+            k //= 2
+
+    def run(self, meshes, op=capi.OP_VOID, sdf=True, record_passes=False):
+        """The CLI loop (apps/cli/main.cpp:92-218) without leaving the device."""
+        for i, m in enumerate(meshes):
+            self.voxelize(m, self.grid_a if i == 0 else self.grid_b)
+            if i > 0 and op != capi.OP_VOID:
+                self.csg(op)
+        if sdf:
+            self.jfa(record_passes)
+
+    def words_host(self) -> np.ndarray:
+        return self.grid_a.cpu().numpy().view(np.uint32)
+
+    def sdf_host(self) -> np.ndarray:
+        return self.sdf.cpu().numpy()

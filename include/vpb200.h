@@ -1,0 +1,129 @@
+/* vpb200 — C ABI of the B200-native voxel pipeline (voxelize -> CSG -> JFA signed squared distance).
+ *
+ * This is the drop-in boundary for the hot path of bigmat18/cuda-mesh-voxelization (vplib):
+ * every entry point names the reference interface it replaces (paths relative to the reference
+ * repository).  Plain pointers and sizes only; no C++/torch types.  All functions return 0 on
+ * success or a negative vpb_status; vpb_last_error() gives the message of the last failure on the
+ * calling thread.  Nothing here ever falls back to a CPU implementation: without a usable
+ * sm_100 device every compute call fails with VPB_ERR_CUDA.
+ *
+ * Data layouts (identical to vplib's):
+ *   occupancy  uint32_t words[ceil(N^3/32)], voxel (x,y,z) is bit (i % 32) of word (i / 32),
+ *              i = x + N*y + N*N*z, bit 0 = lowest x            (vplib/src/grid/voxels_grid.h:116-129)
+ *   sdf        float[N^3], x fastest; SIGNED SQUARED distance, + inside, - outside, 0 on the seed
+ *              shell, +-INF when the grid holds no seed          (vplib/src/jfa/sequential.cpp:56-59,108)
+ *   seeds      uint32_t[N^3]: x | y<<10 | z<<20 of the nearest seed voxel, 0xFFFFFFFF = none (N <= 1024)
+ */
+#ifndef VPB200_H
+#define VPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VPB_API __attribute__((visibility("default")))
+#else
+#define VPB_API
+#endif
+
+typedef enum vpb_status {
+    VPB_OK = 0,
+    VPB_ERR_ARG = -1,     /* bad argument (null pointer, N == 0, unsupported N, bad op/mode) */
+    VPB_ERR_CUDA = -2,    /* CUDA runtime failure, including "no device" */
+    VPB_ERR_NOMEM = -3,   /* device or pinned-host allocation failed */
+    VPB_ERR_STATE = -4    /* vpb_init not called / already shut down */
+} vpb_status;
+
+/* CSG operator numbering == the reference's `enum class CSG::Op` and the CLI's -p (vplib/src/csg/csg.h:10-12). */
+enum { VPB_OP_VOID = 0, VPB_OP_UNION = 1, VPB_OP_INTERSECTION = 2, VPB_OP_DIFFERENCE = 3 };
+
+/* Voxelization mode.  SOLID == the reference's X-ray parity fill (vplib/src/vox/sequential.cpp:16-57).
+ * SURFACE == the seed shell of the solid (set voxels with an empty or out-of-grid 26-neighbour,
+ * vplib/src/jfa/sequential.cpp:36-60) — the only surface set the reference defines. */
+enum { VPB_MODE_SOLID = 0, VPB_MODE_SURFACE = 1 };
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces the implicit context the reference sets up with cudaSetDevice(0) (apps/cli/main.cpp:22-23)
+ * and the per-call cudaMalloc/cudaFree churn of CudaPtr<T> (vplib/src/cuda_ptr.h:14-93): one stream and
+ * a growing device/pinned workspace are kept per process.  One caller thread at a time, like vplib. */
+VPB_API int vpb_init(int device);
+VPB_API void vpb_shutdown(void);
+VPB_API const char* vpb_last_error(void);
+VPB_API int vpb_device_count(void);
+/* Number of this library's kernel launches since vpb_init (bench.py's `gpu_launches`). */
+VPB_API uint64_t vpb_kernel_launches(void);
+/* Milliseconds of the stages of the last *_host / pipeline call, CUDA-event timed:
+ * out[0] H2D, out[1] kernels, out[2] D2H.  Mirrors the reference's "[...::Memory]"/"[...::Processing]" split. */
+VPB_API int vpb_last_timing(float out[3]);
+
+/* ---- host-buffer stage calls: what VOX/CSG/JFA::Compute bind to -------------------------------- */
+
+/* Replaces VOX::Compute<type,T>(HostVoxelsGrid<T>&, const Mesh&)        (vplib/src/vox/vox.h:107-111).
+ * verts_xyz = Mesh::Coords (AoS float3), tri_idx = Mesh::FacesCoords, n_tris = FacesCoords.size()/3
+ * (the sequential oracle's count, vox/sequential.cpp:16).  words_out is overwritten. */
+VPB_API int vpb_voxelize_host(const float* verts_xyz, uint64_t n_verts, const uint32_t* tri_idx, uint64_t n_tris,
+                              uint32_t n, float voxel_size, const float origin[3], int mode, uint32_t* words_out);
+
+/* Replaces CSG::Compute<type,T,func>(grid1, grid2, Op)                   (vplib/src/csg/csg.h:35-36):
+ * a = a | b, a & b or a & ~b word-wise; result in a, b untouched. */
+VPB_API int vpb_csg_host(uint32_t* a_inout, const uint32_t* b, uint32_t n, int op);
+
+/* Replaces JFA::Compute<type,T>(HostVoxelsGrid<T>&, HostGrid<float>&)   (vplib/src/jfa/jfa.h:42-43).
+ * sdf_out is fully overwritten (the reference expects it pre-filled with -INF, apps/cli/main.cpp:200, and
+ * leaves unreached voxels at that value; we write -INF/+INF there ourselves).  nearest_seed_out may be NULL. */
+VPB_API int vpb_jfa_host(const uint32_t* words, uint32_t n, float voxel_size, const float origin[3],
+                         float* sdf_out, uint32_t* nearest_seed_out);
+
+/* Whole CLI pipeline in one call (apps/cli/main.cpp:92-218): voxelize every mesh in the shared frame, fold
+ * grids[0] = op(grids[0], grids[i]) for i = 1.., then (if sdf_out) JFA on grids[0].  Grids stay on the device
+ * between stages.  words_out (optional) receives grids[0]. */
+VPB_API int vpb_pipeline_host(int n_meshes, const float* const* verts_xyz, const uint64_t* n_verts,
+                              const uint32_t* const* tri_idx, const uint64_t* n_tris, uint32_t n, float voxel_size,
+                              const float origin[3], int op, uint32_t* words_out, float* sdf_out);
+
+/* ---- device-pointer calls: the metric path and the building blocks of the z-slab multi-GPU driver ----
+ * All pointers are device pointers in the current context (any allocator, e.g. torch); `stream` is a
+ * cudaStream_t (NULL = the library's own stream).  Calls are asynchronous on that stream.
+ * A slab is the z-range [z0, z1) of the N^3 grid; single-GPU callers pass z0 = 0, z1 = N.           */
+
+/* bytes of scratch vpb_voxelize_dev needs (large-triangle queue, padded rows when N % 32 != 0) */
+VPB_API size_t vpb_voxelize_scratch_bytes(uint32_t n, uint64_t n_tris, uint32_t z0, uint32_t z1);
+/* words_slab: ceil(N*N*(z1-z0)/32) words, overwritten with the slab's solid occupancy. */
+VPB_API int vpb_voxelize_dev(const float* verts_xyz, uint64_t n_verts, const uint32_t* tri_idx, uint64_t n_tris,
+                             uint32_t n, float voxel_size, const float origin[3], uint32_t z0, uint32_t z1,
+                             uint32_t* words_slab, void* scratch, size_t scratch_bytes, void* stream);
+VPB_API int vpb_csg_dev(uint32_t* a_inout, const uint32_t* b, uint64_t n_words, int op, void* stream);
+/* shell_out = seed shell of `words` (full N^3 grid), both dense bit grids. */
+VPB_API int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell_out, void* stream);
+
+/* JFA state: one 32-bit word per voxel (packed nearest-seed coordinates, 0 = none), N <= 1024. */
+VPB_API size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1);
+/* Seed extraction for slab [z0,z1) from the FULL occupancy grid (needs planes z0-1 and z1). */
+VPB_API int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state_slab,
+                             void* stream);
+/* One flood pass with step k over slab [z0,z1).  src_below/src_mid/src_above point at the state of plane
+ * (z0 - k), z0 and (z0 + k) respectively, each followed by the next (z1-z0-1) planes; planes outside the grid
+ * are never dereferenced, so the pointer may be anything there.  On one GPU: mid = in, below = in - k*N*N,
+ * above = in + k*N*N.  If sdf_slab != NULL this is the final pass: the signed squared distance of the result is
+ * written INSTEAD of dst_slab (sign from words_full), and seeds_slab (optional) gets the public seed encoding. */
+VPB_API int vpb_jfa_pass_dev(const uint32_t* src_below, const uint32_t* src_mid, const uint32_t* src_above,
+                             uint32_t* dst_slab, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float voxel_size,
+                             const float origin[3], const uint32_t* words_full, float* sdf_slab, uint32_t* seeds_slab,
+                             void* stream);
+/* state -> sdf without a flood pass (N == 1, or callers that ran the passes themselves). */
+VPB_API int vpb_jfa_finalize_dev(const uint32_t* state_slab, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
+                                 const float origin[3], const uint32_t* words_full, float* sdf_slab,
+                                 uint32_t* seeds_slab, void* stream);
+/* Whole single-GPU JFA: seed extraction + all passes k = N/2..1 + signed output.
+ * state_a/state_b: two buffers of vpb_jfa_state_bytes(n, 0, n). */
+VPB_API int vpb_jfa_dev(const uint32_t* words_full, uint32_t n, float voxel_size, const float origin[3],
+                        uint32_t* state_a, uint32_t* state_b, float* sdf_out, uint32_t* seeds_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPB200_H */

@@ -1,0 +1,186 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden digests.
+Bit-exact for occupancy / CSG / seeds; the SDF is compared as raw float32 bit patterns (stricter than the
+1e-5 relative tolerance north_star allows)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vpb():
+    from cuda_mesh_voxelization_b200 import capi
+    capi.init(0)
+    yield capi
+    capi.shutdown()
+
+
+def _frame(oracle, meshes, names, n):
+    return oracle.frame(np.concatenate([meshes[m][0] for m in names]), n)
+
+
+def _public_seeds(oracle_seeds, n):
+    """oracle linear index -> public encoding x | y<<10 | z<<20 (0xFFFFFFFF = none)."""
+    s = oracle_seeds
+    none = s == np.uint64(0xFFFFFFFFFFFFFFFF)
+    x, y, z = s % n, (s // n) % n, s // (n * n)
+    out = (x | (y << np.uint64(10)) | (z << np.uint64(20))).astype(np.uint32)
+    out[none] = 0xFFFFFFFF
+    return out
+
+
+GOLDEN_SMALL = ["d20_n32", "d20_n48", "d20_n64", "sphere_n32", "sphere_n40", "sphere_n64", "torus_n32", "torus_n33",
+                "torus_n64", "bunny_n64", "bunny_n100", "bunny_n128", "bimba_n64", "sphere_union_torus_n64",
+                "sphere_inter_torus_n64", "sphere_diff_torus_n64", "bimba_union_bunny_n64", "bimba_inter_bunny_n64",
+                "bimba_diff_bunny_n64", "bimba_union_bunny_n256", "bunny_n512_vox"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_SMALL)
+def test_stage_calls_match_reference_digests(name, golden, meshes, oracle, vpb):
+    """vpb_voxelize_host / vpb_csg_host / vpb_jfa_host against the reference's own -t 0 digests."""
+    rec = golden[name]
+    n, op = rec["n"], rec["op"]
+    origin, vs = _frame(oracle, meshes, rec["meshes"], n)
+    grids = []
+    for m, g in zip(rec["meshes"], rec["grids"]):
+        w = vpb.voxelize_host(*meshes[m], n, vs, origin)
+        assert oracle.popcount(w) == g["popcount"]
+        assert f"{oracle.fnv(w):016x}" == g["fnv"]
+        grids.append(w)
+    acc = grids[0]
+    for g in grids[1:]:
+        acc = vpb.csg_host(acc, g, n, op)
+    assert f"{oracle.fnv(acc):016x}" == rec["result"]["fnv"]
+    if "sdf" in rec:
+        sdf = vpb.jfa_host(acc, n, vs, origin)
+        assert int((sdf == 0).sum()) == rec["sdf"]["seeds"]
+        assert f"{oracle.fnv(sdf):016x}" == rec["sdf"]["fnv"]
+
+
+@pytest.mark.parametrize("mesh,n", [("d20", 32), ("sphere", 40), ("torus", 64), ("bunny", 96), ("bimba", 128)])
+def test_jfa_bits_and_seeds_match_oracle(mesh, n, meshes, oracle, vpb):
+    v, t = meshes[mesh]
+    origin, vs = oracle.frame(v, n)
+    words = vpb.voxelize_host(v, t, n, vs, origin)
+    assert np.array_equal(words, oracle.voxelize(v, t, n, vs, origin))
+    sdf, seeds = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    osdf, oseeds = oracle.jfa(words, n, vs, origin, want_seeds=True)
+    assert np.array_equal(sdf.view(np.uint32), osdf.view(np.uint32))
+    assert np.array_equal(seeds, _public_seeds(oseeds, n))
+    # tolerance form of the same statement, as north_star words it
+    fin = np.isfinite(osdf)
+    assert np.allclose(sdf[fin], osdf[fin], rtol=1e-5, atol=0.0)
+
+
+def test_pipeline_host_matches_stage_calls_and_golden(golden, meshes, oracle, vpb):
+    rec = golden["bimba_union_bunny_n256"]
+    n = rec["n"]
+    origin, vs = _frame(oracle, meshes, rec["meshes"], n)
+    words, sdf = vpb.pipeline_host([meshes[m] for m in rec["meshes"]], n, vs, origin, op=rec["op"])
+    assert f"{oracle.fnv(words):016x}" == rec["result"]["fnv"]
+    assert f"{oracle.fnv(sdf):016x}" == rec["sdf"]["fnv"]
+    t = vpb.last_timing()
+    assert t["kernels_ms"] > 0 and t["d2h_ms"] > 0
+    assert vpb.kernel_launches() > 0
+
+
+def test_surface_mode_is_the_seed_shell(meshes, oracle, vpb):
+    from cuda_mesh_voxelization_b200 import capi
+    for mesh, n in [("torus", 64), ("sphere", 40), ("bunny", 128)]:
+        v, t = meshes[mesh]
+        origin, vs = oracle.frame(v, n)
+        shell = vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE)
+        solid = oracle.voxelize(v, t, n, vs, origin)
+        assert np.array_equal(shell, oracle.seed_shell(solid, n))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 24, 31, 33, 64])
+def test_random_grids_ties_and_edges(n, oracle, vpb):
+    """Random occupancy (dense ties, seeds on the grid border, N = 1..) through CSG + JFA, awkward frame."""
+    rng = np.random.default_rng(n)
+    nw = (n ** 3 + 31) // 32
+    a = rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
+    b = rng.integers(0, 2 ** 32, nw, dtype=np.uint32) & rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
+    tail = n ** 3 % 32
+    if tail:  # keep the padding bits of the last word clear, like a voxelized grid
+        a[-1] &= (1 << tail) - 1
+        b[-1] &= (1 << tail) - 1
+    origin = np.array([0.3, -1.7, 2.9], np.float32)
+    for op in (1, 2, 3):
+        got = vpb.csg_host(a.copy(), b, n, op)
+        want = oracle.csg(a, b, n, op)
+        assert np.array_equal(got, want)
+        sdf, seeds = vpb.jfa_host(got, n, 0.173, origin, want_seeds=True)
+        osdf, oseeds = oracle.jfa(want, n, 0.173, origin, want_seeds=True)
+        assert np.array_equal(sdf.view(np.uint32), osdf.view(np.uint32))
+        assert np.array_equal(seeds, _public_seeds(oseeds, n))
+
+
+def test_empty_and_full_grids(oracle, vpb):
+    n = 32
+    nw = n ** 3 // 32
+    o = np.zeros(3, np.float32)
+    empty = np.zeros(nw, np.uint32)
+    sdf = vpb.jfa_host(empty, n, 1.0, o)
+    assert np.all(np.isneginf(sdf))                       # reference: every voxel stays at the CLI's -INF
+    full = np.full(nw, 0xFFFFFFFF, np.uint32)
+    sdf = vpb.jfa_host(full, n, 1.0, o)
+    assert np.array_equal(sdf.view(np.uint32), oracle.jfa(full, n, 1.0, o).view(np.uint32))
+    # empty mesh -> empty grid
+    w = vpb.voxelize_host(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), n, 1.0, o)
+    assert not w.any()
+
+
+def test_large_triangles_take_the_queued_path(meshes, oracle, vpb):
+    """20 huge triangles at 256^3: every triangle covers ~10^4 (y,z) cells and goes through vox_raster_large."""
+    v, t = meshes["d20"]
+    for n in (256, 200):
+        origin, vs = oracle.frame(v, n)
+        assert np.array_equal(vpb.voxelize_host(v, t, n, vs, origin), oracle.voxelize(v, t, n, vs, origin))
+
+
+def test_triangles_outside_the_frame_are_clipped(meshes, oracle, vpb):
+    """A frame that cuts the mesh: cells outside the grid are skipped, startX < 0 clamps (oracle header)."""
+    v, t = meshes["sphere"]
+    n = 48
+    origin = np.array([-0.4, -0.6, -0.2], np.float32)
+    vs = np.float32(0.03)
+    got = vpb.voxelize_host(v, t, n, vs, origin)
+    want, stats = oracle.voxelize(v, t, n, vs, origin, return_stats=True)
+    assert stats[2] > 0 and stats[4] > 0      # the undefined-in-the-reference cases really fire here
+    assert np.array_equal(got, want)
+
+
+def test_vplib_mirror_reads_like_the_reference(meshes, oracle, vpb):
+    from cuda_mesh_voxelization_b200 import CSG, JFA, VOX, HostGrid, HostVoxelsGrid, Mesh, Types, shared_frame
+    n = 64
+    ms = [Mesh("bimba", *meshes["bimba"]), Mesh("bunny", *meshes["bunny"])]
+    origin, vs = shared_frame(ms, n)
+    o2, vs2 = oracle.frame(np.concatenate([m.Coords for m in ms]), n)
+    assert np.array_equal(origin, o2) and vs == vs2
+    grids = []
+    for m in ms:
+        g = HostVoxelsGrid(n, vs)
+        g.View().SetOrigin(*origin)
+        VOX.Compute(Types.B200, g, m)
+        grids.append(g)
+    CSG.Compute(Types.B200, grids[0], grids[1], CSG.Difference())
+    sdf = HostGrid(n, -np.inf)
+    JFA.Compute(Types.B200, grids[0], sdf)
+    want = oracle.csg(oracle.voxelize(*meshes["bimba"], n, vs, origin), oracle.voxelize(*meshes["bunny"], n, vs, origin), n, 3)
+    assert np.array_equal(grids[0].words, want)
+    assert np.array_equal(sdf.data.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
+    assert grids[0].View().Voxel(n // 2, n // 2, n // 2) == bool(grids[0].to_bool()[n // 2, n // 2, n // 2])
+
+
+def test_benchmark_mesh_1348128_faces_512(meshes, oracle, vpb):
+    """BASELINE config 3 voxelization (1 348 128-face subdivided bunny at 512^3) against the oracle."""
+    from cuda_mesh_voxelization_b200 import meshgen
+    v, t = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
+    assert t.shape[0] == 1348128 and meshgen.is_closed(t)
+    n = 512
+    origin, vs = oracle.frame(v, n)
+    got = vpb.voxelize_host(v, t, n, vs, origin)
+    want, stats = oracle.voxelize(v, t, n, vs, origin, return_stats=True)
+    assert stats[2] == 0 and stats[3] == 0 and stats[4] == 0
+    assert np.array_equal(got, want)
