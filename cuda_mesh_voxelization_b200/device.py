@@ -22,7 +22,11 @@ def _ptr(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream as a cudaStream_t.  The legacy default stream's handle is 0, which the C ABI reads
+    as "use the library's own stream"; pass cudaStreamLegacy (0x1) instead so that the launches really are ordered
+    (and event-timed) on torch's stream."""
+    h = torch.cuda.current_stream().cuda_stream
+    return ctypes.c_void_p(h if h else 1)
 
 
 class DeviceMesh:
