@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    link = [nvcc, "-ccbin", host_cxx, "-shared", "-o", LIB, *objs]
+    link = [nvcc, "-ccbin", host_cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -1,0 +1,437 @@
+// JFA flood pass, tiled "z-march" version for sm_100a (N % 64 == 0, N <= 1024; k >= 64 or k in {1,2,..,32}).
+//
+// Why this shape.  A flood pass is a 27-point stencil at stride k, i.e. an ordinary 3x3x3 stencil on each of the k^3
+// interleaved lattices (SURVEY §7 "hard parts").  With a 4-byte state it moves only 8 B/voxel of compulsory HBM
+// traffic, but evaluating the reference's float distance for 27 candidates costs far more issue slots than that
+// traffic costs time (profiles/r01_v0_gather_summary.md: 44 ms/pass for the direct gather).  This kernel therefore
+// minimises INSTRUCTIONS per voxel while keeping DRAM traffic compulsory (ncu: 1.04 GB/pass at 512^3 = 8 B/voxel):
+//   * a CTA owns 8 lattice rows x 64 voxels in x and marches along its z-lattice column;
+//   * each new input plane is staged ONCE into shared memory already converted to the seeds' world coordinates
+//     (three float tables px/py/pz, the reference's origin + idx*voxelSize), "no seed" as z = +INF;
+//   * a thread owns two x-adjacent voxels and keeps, for the two older live planes, the partial sums
+//     (dx*dx + dy*dy) of its 9 (dx,dy) candidates in registers — they do not depend on z, so each input voxel's
+//     partial is computed once and used for the three outputs z-k, z, z+k it feeds;
+//   * all float work is done two voxels at a time with the sm_100 packed-FP32 instructions (FADD2 / FFMA2:
+//     individually rounded lanes, bit-identical to scalar code — see sq2() for the one ptxas pitfall);
+//   * when the y-lattice has <= 8 points (large k) a CTA takes whole lattice columns of several y-residues instead
+//     of a tile with halo rows, and out-of-grid planes are never staged.
+// Candidate order (dz outer, dy, dx inner, own value first, strict <) and every rounding are the reference's
+// (vplib/src/jfa/sequential.cpp:84-113, jfa/jfa.h:19-20).
+#include "common.cuh"
+
+namespace vpb {
+
+int jfa_pass_gather_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                           float* sdf, uint32_t* seeds, cudaStream_t st);
+
+namespace {
+
+constexpr int TW = 8;            // warps per CTA == output rows per CTA
+constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
+constexpr int ROWS = TW + 2;     // staged rows per plane: tile mode 1 halo row each side; column mode 8 rows + 1 dummy
+constexpr int THREADS = TW * 32;
+constexpr int MAXN = 1024;
+
+template <int SS>
+struct Tile {
+    static constexpr int W = SEG + 2 * SS;           // staged window per row
+    static constexpr int PLANE = ROWS * W;           // entries per staged plane
+    static constexpr int U = (W + 31) / 32;          // own-row entries per lane
+    static constexpr int HV = (2 * W + THREADS - 1) / THREADS;   // halo-row entries per thread
+    // shared memory layout (floats / words)
+    static constexpr int OFF_LUT = 0;                // px, py, pz: 3 * MAXN
+    static constexpr int OFF_FX = 3 * MAXN;
+    static constexpr int OFF_FY = OFF_FX + PLANE;
+    static constexpr int OFF_FZ = OFF_FY + PLANE;
+    static constexpr int OFF_PS = OFF_FZ + PLANE;    // ring of 3 packed planes
+    static constexpr int WORDS = OFF_PS + 3 * PLANE;
+    static constexpr size_t BYTES = (size_t)WORDS * 4;
+};
+
+struct PassArgs {
+    const uint32_t* src[3];   // below / mid / above (see vpb_jfa_pass_dev)
+    uint32_t* dst;
+    const uint32_t* words;    // occupancy (FINAL only)
+    float* sdf;               // FINAL only
+    uint32_t* seeds;          // FINAL only, optional
+    Frame f;
+    uint32_t z0, T;           // slab
+    int k;
+    int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
+    int lz;                   // outputs per march segment
+    int tiles_y, segs_z;
+    int column_mode;          // y lattice has <= 8 points: CTA = whole columns of `8 / lp` y-residues
+    int lp, ly;               // column mode: padded (power of two) and true lattice length in y
+    float neg_zero;           // -0.0f, deliberately a RUNTIME value: see sq2()
+};
+
+__device__ __forceinline__ float2 ld2(const float* p, bool aligned) {
+    if (aligned) return *reinterpret_cast<const float2*>(p);
+    return make_float2(p[0], p[1]);
+}
+
+// x*x for two lanes, individually rounded.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with
+// --fmad=false and explicit .rn (scalar mul.rn/add.rn are left alone), which would break bit-exactness with the
+// reference's unfused ((dx*dx)+(dy*dy))+(dz*dz).  Writing the product as fma(x, x, nz) with nz = -0.0f known only at
+// run time gives the identical rounding (p + -0 == p for every p, including p == +0) and cannot be merged with the
+// following add.
+__device__ __forceinline__ float2 sq2(float2 x, float2 nz) { return __ffma2_rn(x, x, nz); }
+
+// Registers of one thread: two cached planes x 9 candidates (dy,dx) x 2 voxels.  The third live plane (the newest)
+// is converted while it is scanned and overwrites the oldest cached plane, which has just been scanned.
+struct Cache {
+    float2 xy[2][9];
+    float2 fz[2][9];
+    uint32_t any[2];   // SPARSE: bit c set if any lane of the warp has a valid candidate c in that plane
+};
+
+template <int SS, bool FINAL, bool SPARSE>
+struct March {
+    using TL = Tile<SS>;
+    static constexpr bool ALIGNED = (SS % 2) == 0;
+
+    // Per-thread, plane-invariant description of the entries this thread stages.
+    struct Stager {
+        int own_off[TL::U];      // offset of own-row entry u inside a plane (y*n + x), -1 = outside the grid
+        int halo_off[TL::HV];    // same for the halo-row entries (tile mode only)
+        int own_sm;              // shared index of own-row entry 0 (entry u is at +32u)
+        int halo_sm[TL::HV];     // shared index of halo entries, -1 = none
+    };
+
+    static __device__ __forceinline__ int gx_of(int i, int xs, int k) {
+        // window: contiguous [xs-k, xs+64+k) when k < 64, three 64-wide segments at xs-k, xs, xs+k otherwise
+        return (SS < 64) ? (xs - SS + i) : (xs + (i / SEG - 1) * k + (i % SEG));
+    }
+
+    static __device__ __forceinline__ void prefetch(uint32_t (&own)[TL::U], uint32_t (&halo)[TL::HV], const Stager& s,
+                                                    const uint32_t* __restrict__ plane, bool column_mode) {
+#pragma unroll
+        for (int u = 0; u < TL::U; ++u) own[u] = s.own_off[u] >= 0 ? __ldg(plane + s.own_off[u]) : 0u;
+        if (!column_mode) {
+#pragma unroll
+            for (int v = 0; v < TL::HV; ++v) halo[v] = s.halo_off[v] >= 0 ? __ldg(plane + s.halo_off[v]) : 0u;
+        }
+    }
+
+    static __device__ __forceinline__ void put(float* sm, uint32_t* ps, int e, uint32_t s) {
+        const char* lut = reinterpret_cast<const char*>(sm + TL::OFF_LUT);
+        sm[TL::OFF_FX + e] = *reinterpret_cast<const float*>(lut + (s & 0xFFCu));
+        sm[TL::OFF_FY + e] = *reinterpret_cast<const float*>(lut + 4 * MAXN + ((s >> 10) & 0xFFCu));
+        const float z = *reinterpret_cast<const float*>(lut + 8 * MAXN + ((s >> 20) & 0xFFCu));
+        sm[TL::OFF_FZ + e] = s ? z : INFINITY;   // one infinite coordinate makes the whole distance +INF
+        ps[e] = s;
+    }
+
+    // registers -> shared: world coordinates of the seeds + packed ring slot
+    static __device__ __forceinline__ void stage(const uint32_t (&own)[TL::U], const uint32_t (&halo)[TL::HV],
+                                                 const Stager& s, float* sm, int ring_slot, bool column_mode, int lane) {
+        uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS) + ring_slot * TL::PLANE;
+#pragma unroll
+        for (int u = 0; u < TL::U; ++u)
+            if (TL::W % 32 == 0 || lane + 32 * u < TL::W) put(sm, ps, s.own_sm + 32 * u, own[u]);
+        if (!column_mode) {
+#pragma unroll
+            for (int v = 0; v < TL::HV; ++v)
+                if (s.halo_sm[v] >= 0) put(sm, ps, s.halo_sm[v], halo[v]);
+        }
+    }
+
+    // candidate cc of the staged (newest) plane -> cache slot SLOT
+    template <int SLOT>
+    static __device__ __forceinline__ bool convert(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
+                                                   float2 nz, int cc) {
+        const int off = tb[cc / 3] + (cc % 3) * SS;
+        const float2 sx = ld2(sm + TL::OFF_FX + off, ALIGNED);
+        const float2 sy = ld2(sm + TL::OFF_FY + off, ALIGNED);
+        const float2 sz = ld2(sm + TL::OFF_FZ + off, ALIGNED);
+        const float2 ddx = __fadd2_rn(sx, nqx);          // seed - voxel (the exact negation is folded into nq*)
+        const float2 ddy = __fadd2_rn(sy, nqy);
+        c.xy[SLOT][cc] = __fadd2_rn(sq2(ddx, nz), sq2(ddy, nz));
+        c.fz[SLOT][cc] = sz;
+        if (!SPARSE) return true;
+        return __any_sync(0xffffffffu, (sz.x != INFINITY) || (sz.y != INFINITY));
+    }
+
+    // a plane outside the grid: nothing was staged, every candidate is "no seed"
+    template <int SLOT>
+    static __device__ __forceinline__ void invalidate(Cache& c) {
+#pragma unroll
+        for (int cc = 0; cc < 9; ++cc) {
+            c.xy[SLOT][cc] = make_float2(0.0f, 0.0f);
+            c.fz[SLOT][cc] = make_float2(INFINITY, INFINITY);
+        }
+        c.any[SLOT] = 0;
+    }
+
+    // priming: the first two planes of a march only fill the cache
+    template <int SLOT>
+    static __device__ __forceinline__ void consume(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
+                                                   float2 nz) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int cc = 0; cc < 9; ++cc)
+            if (convert<SLOT>(c, sm, tb, nqx, nqy, nz, cc)) any |= 1u << cc;
+        c.any[SLOT] = any;
+    }
+
+    template <int SLOT>
+    static __device__ __forceinline__ void eval(const Cache& c, int cc, float2 nqz, float2 nz, int code, float2& best,
+                                                int& ia, int& ib) {
+        const float2 ddz = __fadd2_rn(c.fz[SLOT][cc], nqz);
+        const float2 d = __fadd2_rn(c.xy[SLOT][cc], sq2(ddz, nz));   // ((dx*dx)+(dy*dy)) + (dz*dz)
+        if (d.x < best.x) ia = code;                                 // strict <: the earlier candidate keeps ties
+        if (d.y < best.y) ib = code;
+        best.x = fminf(best.x, d.x);
+        best.y = fminf(best.y, d.y);
+    }
+
+    // One output plane.  Cache slot RS holds plane z-k on entry and receives plane z+k; slot 1-RS holds plane z.
+    // ring_p/q/r: word offsets of the three planes inside the packed ring.
+    template <int RS>
+    static __device__ __forceinline__ void emit(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
+                                                float2 nz, float nqz_s, int ring_p, int ring_q, int ring_r, bool r_ok,
+                                                const PassArgs& a, int zl, int gy, int xs, int lane) {
+        constexpr int QS = 1 - RS;
+        const float2 nqz = make_float2(nqz_s, nqz_s);
+        // own value first (sequential.cpp:83: bestDistance = sdf(voxel)); +INF while the voxel has no seed
+        const float2 dz0 = __fadd2_rn(c.fz[QS][4], nqz);
+        float2 best = __fadd2_rn(c.xy[QS][4], sq2(dz0, nz));
+        int ia = ring_q + tb[1] + SS, ib = ia;
+#pragma unroll
+        for (int cc = 0; cc < 9; ++cc) {                       // plane z-k
+            if (SPARSE && !((c.any[RS] >> cc) & 1u)) continue;
+            eval<RS>(c, cc, nqz, nz, ring_p + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 9; ++cc) {                       // plane z, own voxel skipped
+            if (cc == 4) continue;
+            if (SPARSE && !((c.any[QS] >> cc) & 1u)) continue;
+            eval<QS>(c, cc, nqz, nz, ring_q + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
+        }
+        if (r_ok) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int cc = 0; cc < 9; ++cc) {                   // plane z+k: convert into the freed slot, then scan
+                if (convert<RS>(c, sm, tb, nqx, nqy, nz, cc)) {
+                    any |= 1u << cc;
+                    eval<RS>(c, cc, nqz, nz, ring_r + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
+                }
+            }
+            c.any[RS] = any;
+        } else {
+            invalidate<RS>(c);
+        }
+        const uint32_t* ps = reinterpret_cast<const uint32_t*>(sm + TL::OFF_PS);
+        const uint32_t sa = ps[ia], sb = ps[ib + 1];
+        const int n = (int)a.f.n;
+        const size_t v = ((size_t)zl * n + gy) * n + xs + 2 * lane;
+        if (!FINAL) {
+            *reinterpret_cast<uint2*>(a.dst + v) = make_uint2(sa, sb);
+        } else {
+            const size_t bit = ((size_t)(zl + a.z0) * n + gy) * n + xs + 2 * lane;
+            const uint32_t w = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
+            const float ma = sa ? best.x : INFINITY, mb = sb ? best.y : INFINITY;
+            *reinterpret_cast<float2*>(a.sdf + v) = make_float2((w & 1u) ? ma : -ma, (w & 2u) ? mb : -mb);
+            if (a.seeds) *reinterpret_cast<uint2*>(a.seeds + v) = make_uint2(jfa_public(sa), jfa_public(sb));
+        }
+    }
+
+    static __device__ __forceinline__ void run(const PassArgs& a) {
+        extern __shared__ float sm[];
+        const int n = (int)a.f.n, k = a.k;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const bool col = a.column_mode != 0;
+        // world-position tables p(i) = origin + float(i) * voxelSize (sequential.cpp:32-34,78-80)
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            const float t = __fmul_rn((float)i, a.f.vs);
+            sm[TL::OFF_LUT + i] = __fadd_rn(a.f.ox, t);
+            sm[TL::OFF_LUT + MAXN + i] = __fadd_rn(a.f.oy, t);
+            sm[TL::OFF_LUT + 2 * MAXN + i] = __fadd_rn(a.f.oz, t);
+        }
+        // ---- tile coordinates -------------------------------------------------------------------------------
+        const int xs = blockIdx.x * SEG;
+        const int rz = blockIdx.z / a.segs_z, sz = blockIdx.z - rz * a.segs_z;
+        const int zl0 = rz + sz * a.lz * k;                     // slab-local z of the first output plane
+        int steps = 0;                                          // outputs of this march segment inside the slab
+        for (int j = 0; j < a.lz; ++j) if (zl0 + j * k < (int)a.T) ++steps;
+        if (steps == 0) return;
+        // own output row of this warp, staged row index of the rows it reads for dy = -1, 0, +1
+        int gy, row[3], own_row;
+        bool row_ok;
+        if (!col) {
+            const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
+            gy = ry + (ty * TW + warp) * k;
+            row_ok = gy < n;
+            own_row = warp + 1;
+            row[0] = warp; row[1] = warp + 1; row[2] = warp + 2;
+        } else {
+            const int res_per_cta = TW / a.lp;
+            const int g = warp / a.lp, j = warp - g * a.lp;
+            const int ry = blockIdx.y * res_per_cta + g;
+            gy = ry + j * k;
+            row_ok = ry < k && j < a.ly && gy < n;
+            own_row = warp;
+            row[1] = warp;
+            row[0] = (j - 1 >= 0) ? warp - 1 : TW;              // row TW is the dummy "no seed" row
+            row[2] = (j + 1 < a.ly) ? warp + 1 : TW;
+        }
+        // ---- what this thread stages (plane-invariant) ---------------------------------------------------------
+        Stager st;
+        st.own_sm = own_row * TL::W + lane;
+#pragma unroll
+        for (int u = 0; u < TL::U; ++u) {
+            const int i = lane + 32 * u;
+            const int gx = gx_of(i, xs, k);
+            st.own_off[u] = (row_ok && i < TL::W && gx >= 0 && gx < n) ? gy * n + gx : -1;
+        }
+#pragma unroll
+        for (int v = 0; v < TL::HV; ++v) {
+            st.halo_off[v] = -1;
+            st.halo_sm[v] = -1;
+            const int h = (int)threadIdx.x + THREADS * v;
+            if (!col && h < 2 * TL::W) {
+                const int top = h >= TL::W;                     // 0: staged row 0, 1: staged row 9
+                const int i = h - top * TL::W;
+                const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
+                const int hy = ry + (ty * TW + (top ? TW : -1)) * k;
+                const int gx = gx_of(i, xs, k);
+                st.halo_sm[v] = (top ? (TW + 1) : 0) * TL::W + i;
+                if (hy >= 0 && hy < n && gx >= 0 && gx < n) st.halo_off[v] = hy * n + gx;
+            }
+        }
+        if (col) {  // the dummy row never changes: "no seed" in the float buffers and in all three ring slots
+            uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS);
+            for (int i = threadIdx.x; i < TL::W; i += THREADS) {
+                sm[TL::OFF_FX + TW * TL::W + i] = 0.0f;
+                sm[TL::OFF_FY + TW * TL::W + i] = 0.0f;
+                sm[TL::OFF_FZ + TW * TL::W + i] = INFINITY;
+                ps[TW * TL::W + i] = 0u; ps[TL::PLANE + TW * TL::W + i] = 0u; ps[2 * TL::PLANE + TW * TL::W + i] = 0u;
+            }
+        }
+        const size_t plane_sz = (size_t)n * n;
+        __syncthreads();
+        const float* lut = sm + TL::OFF_LUT;
+        const int x0 = xs + 2 * lane;
+        const float2 nqx = make_float2(-lut[x0], -lut[x0 + 1]);
+        const float qy_s = row_ok ? lut[MAXN + gy] : 0.0f;
+        const float2 nqy = make_float2(-qy_s, -qy_s);
+        const float2 nz = make_float2(a.neg_zero, a.neg_zero);
+        const int tb[3] = {row[0] * TL::W + 2 * lane, row[1] * TL::W + 2 * lane, row[2] * TL::W + 2 * lane};
+
+        Cache c;
+        uint32_t own[TL::U], halo[TL::HV];
+        // plane p (p = -1 .. steps) of the march: slab-local z = zl0 + p*k
+        auto plane_ptr = [&](int p, bool& ok) -> const uint32_t* {
+            const int zl = zl0 + p * k;
+            const int gz = zl + (int)a.z0;
+            ok = gz >= 0 && gz < n;
+            if (a.contiguous) return a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz;
+            return (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;   // steps == 1 here
+        };
+        bool ok_next;
+        const uint32_t* pp = plane_ptr(-1, ok_next);
+        if (ok_next) prefetch(own, halo, st, pp, col);
+        int ring_p = 0, ring_q = 0, ring_r = 0;                 // ring slot (in words) of planes p-2, p-1, p
+#pragma unroll 1
+        for (int p = -1; p <= steps; ++p) {
+            const bool ok = ok_next;
+            ring_p = ring_q; ring_q = ring_r;
+            ring_r = ((p + 1) % 3) * TL::PLANE;
+            if (ok) stage(own, halo, st, sm, (p + 1) % 3, col, lane);
+            __syncthreads();
+            if (p < steps) {
+                pp = plane_ptr(p + 1, ok_next);
+                if (ok_next) prefetch(own, halo, st, pp, col);
+            }
+            if (row_ok) {
+                if (p < 1) {
+                    if (p == -1) { if (ok) consume<0>(c, sm, tb, nqx, nqy, nz); else invalidate<0>(c); }
+                    else         { if (ok) consume<1>(c, sm, tb, nqx, nqy, nz); else invalidate<1>(c); }
+                } else {
+                    const int zl = zl0 + (p - 1) * k;
+                    const float nqz = -lut[2 * MAXN + zl + (int)a.z0];
+                    // plane q lives in cache slot (q+1)&1: the newest plane p replaces plane p-2
+                    if ((p + 1) & 1) emit<1>(c, sm, tb, nqx, nqy, nz, nqz, ring_p, ring_q, ring_r, ok, a, zl, gy, xs, lane);
+                    else emit<0>(c, sm, tb, nqx, nqy, nz, nqz, ring_p, ring_q, ring_r, ok, a, zl, gy, xs, lane);
+                }
+            }
+            __syncthreads();
+        }
+    }
+};
+
+template <int SS, bool FINAL, bool SPARSE>
+__global__ void __launch_bounds__(THREADS, 2) jfa_pass_march(const PassArgs a) { March<SS, FINAL, SPARSE>::run(a); }
+
+template <int SS, bool FINAL, bool SPARSE>
+int launch_one(const PassArgs& a, dim3 grid, cudaStream_t st) {
+    using TL = Tile<SS>;
+    static bool configured = false;
+    if (!configured) {
+        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_march<SS, FINAL, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
+        configured = true;
+    }
+    jfa_pass_march<SS, FINAL, SPARSE><<<grid, THREADS, TL::BYTES, st>>>(a);
+    VPB_LAUNCH_CHECK();
+    return VPB_OK;
+}
+
+template <int SS>
+int launch_ss(const PassArgs& a, dim3 grid, bool fin, bool sparse, cudaStream_t st) {
+    if (fin) return launch_one<SS, true, false>(a, grid, st);
+    if (sparse) return launch_one<SS, false, true>(a, grid, st);
+    return launch_one<SS, false, false>(a, grid, st);
+}
+
+}  // namespace
+
+// Returns VPB_OK after launching, or falls back to the gather kernel for shapes the tile does not cover.
+int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                          uint32_t* seeds, cudaStream_t st) {
+    const uint32_t n = f.n, T = z1 - z0;
+    const bool k_ok = k >= 64 || k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32;
+    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
+    if (n % SEG != 0 || n > MAXN || !k_ok || !align_ok)
+        return jfa_pass_gather_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    PassArgs a;
+    a.src[0] = below; a.src[1] = mid; a.src[2] = above;
+    a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
+    a.f = f; a.z0 = z0; a.T = T; a.k = (int)k;
+    a.neg_zero = -0.0f;
+    const ptrdiff_t kp = (ptrdiff_t)k * n * n;
+    a.contiguous = (above == mid + kp) && (below == mid - kp);
+    const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
+    a.lz = a.contiguous ? (cz < 32 ? cz : 32) : 1;
+    a.segs_z = (cz + a.lz - 1) / a.lz;
+    const int cy = (int)((n + k - 1) / k);                      // lattice points per y column
+    const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
+    unsigned grid_y;
+    a.column_mode = cy <= TW;
+    a.tiles_y = 1; a.lp = TW; a.ly = cy;
+    if (a.column_mode) {
+        a.lp = 1;
+        while (a.lp < cy) a.lp <<= 1;
+        const int res_per_cta = TW / a.lp;
+        grid_y = (res_y + res_per_cta - 1) / res_per_cta;
+    } else {
+        a.tiles_y = (cy + TW - 1) / TW;
+        grid_y = res_y * a.tiles_y;
+    }
+    dim3 grid(n / SEG, grid_y, res_z * a.segs_z);
+    VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
+    const bool fin = sdf != nullptr;
+    const bool sparse = !fin && k >= n / 8;                     // the first passes see few seeds: skip empty candidates
+    switch (k >= 64 ? 64 : (int)k) {
+        case 64: return launch_ss<64>(a, grid, fin, sparse, st);
+        case 32: return launch_ss<32>(a, grid, fin, sparse, st);
+        case 16: return launch_ss<16>(a, grid, fin, sparse, st);
+        case 8: return launch_ss<8>(a, grid, fin, sparse, st);
+        case 4: return launch_ss<4>(a, grid, fin, sparse, st);
+        case 2: return launch_ss<2>(a, grid, fin, sparse, st);
+        default: return launch_ss<1>(a, grid, fin, sparse, st);
+    }
+}
+
+}  // namespace vpb

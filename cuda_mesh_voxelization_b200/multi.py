@@ -1,0 +1,279 @@
+"""z-slab multi-GPU driver: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+Partition.  Rank r owns the planes z in [r*T, (r+1)*T), T = N / world.
+  * voxelization / CSG : the fill axis is +X and rows are x-contiguous, so a z-slab owns whole rows — no parity
+                         carry, no communication.  Every rank rasterises the full mesh clipped to its slab.
+  * occupancy          : all-gathered once (N^3/8 bytes in total) — seed extraction needs one plane either side
+                         and the final pass needs the sign; the bit grid is tiny next to the seed state.
+  * JFA passes         : one halo exchange per pass.  A voxel at z needs planes z-k and z+k:
+        k <  T : k boundary planes from each adjacent rank, received straight into the halo region of an
+                 extended buffer [T/2 | T | T/2 planes] so the pass kernel sees one contiguous z range;
+        k >= T : the whole slab of rank r -/+ k/T (NVSwitch: any peer at full bandwidth), received into two
+                 separate slab buffers (the pass kernel takes three independent plane pointers).
+Results are bit-identical to the single-GPU pipeline by construction (same kernels, same candidate order).
+
+The exchange *schedule* is pure Python (`SlabPlan`) and is exercised on CPU tensors over gloo in
+tests/test_multi_gloo.py; `SlabPipeline` runs it on GPUs.  `LocalComm` emulates the ranks inside one process
+(all slabs on one GPU) so the slab code paths are parity-tested on a single-GPU box as well.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------------------- schedule (pure)
+
+@dataclass(frozen=True)
+class Transfer:
+    peer: int          # rank on the other side
+    src_lo: int        # first slab-local plane of the SENDER's slab that travels
+    count: int         # number of planes
+    role: str          # where it lands on the receiver: "below" or "above"
+
+
+class SlabPlan:
+    def __init__(self, n: int, rank: int, world: int):
+        if n % world != 0:
+            raise ValueError(f"N={n} is not divisible by {world} slabs")
+        self.n, self.rank, self.world = n, rank, world
+        self.T = n // world
+        self.z0, self.z1 = rank * self.T, (rank + 1) * self.T
+        self.H = max(self.T // 2, 1)     # halo capacity of the extended buffer (largest k < T is T/2)
+
+    def steps(self) -> List[int]:
+        out, k = [], self.n // 2
+        while k >= 1:
+            out.append(k)
+            k //= 2
+        return out
+
+    def sends(self, k: int) -> List[Transfer]:
+        """Planes of MY slab other ranks need for a pass with step k."""
+        T, r, W = self.T, self.rank, self.world
+        out = []
+        if k < T:
+            if r + 1 < W:
+                out.append(Transfer(r + 1, T - k, k, "below"))   # my top k planes are their z0-k .. z0-1
+            if r - 1 >= 0:
+                out.append(Transfer(r - 1, 0, k, "above"))       # my bottom k planes are their z1 .. z1+k-1
+        else:
+            if k % T != 0:
+                raise ValueError(f"step {k} is not a multiple of the slab thickness {T}")
+            d = k // T
+            if r + d < W:
+                out.append(Transfer(r + d, 0, T, "below"))
+            if r - d >= 0:
+                out.append(Transfer(r - d, 0, T, "above"))
+        return out
+
+    def recvs(self, k: int) -> List[Transfer]:
+        """What I receive (peer = sender; src_lo/count describe the sender's planes)."""
+        T, r, W = self.T, self.rank, self.world
+        out = []
+        if k < T:
+            if r - 1 >= 0:
+                out.append(Transfer(r - 1, T - k, k, "below"))
+            if r + 1 < W:
+                out.append(Transfer(r + 1, 0, k, "above"))
+        else:
+            d = k // T
+            if r - d >= 0:
+                out.append(Transfer(r - d, 0, T, "below"))
+            if r + d < W:
+                out.append(Transfer(r + d, 0, T, "above"))
+        return out
+
+
+# ----------------------------------------------------------------------------------------- GPU pipeline
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class SlabPipeline:
+    """One rank's share of voxelize -> CSG -> JFA.  `comm` is None (torch.distributed) or a LocalComm."""
+
+    def __init__(self, n, voxel_size, origin, rank, world, device="cuda:0", comm=None, want_seeds=False):
+        import torch
+        from . import capi
+        self.torch, self.capi = torch, capi
+        self.lib = capi.load()
+        if n % 32 or n > 1024:
+            raise ValueError("slab pipeline needs N % 32 == 0 and N <= 1024")
+        self.plan = SlabPlan(n, rank, world)
+        self.n, self.vs = int(n), float(voxel_size)
+        self.origin = np.ascontiguousarray(origin, np.float32)
+        self.device = torch.device(device)
+        self.comm = comm
+        capi.init(self.device.index or 0)
+        p = self.plan
+        self.plane = n * n
+        self.slab_voxels = self.plane * p.T
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.grid_full = torch.zeros(capi.n_words(n), **i32)
+        wslab = self.plane * p.T // 32
+        self.grid_slab = self.grid_full[rank * wslab:(rank + 1) * wslab]     # a view: CSG result lands in place
+        self.grid_b = torch.empty(wslab, **i32)
+        # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
+        self.ext = [torch.zeros((p.H + p.T + p.H) * self.plane, **i32) for _ in range(2)]
+        self.far = [torch.empty(self.slab_voxels, **i32) for _ in range(2)] if world > 1 else [None, None]
+        self.sdf = torch.empty(self.slab_voxels, dtype=torch.float32, device=self.device)
+        self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
+        self.scratch = None
+        self.pass_events = []
+
+    # -- helpers
+    def _o(self):
+        return self.origin.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+    def _stream(self):
+        h = self.torch.cuda.current_stream().cuda_stream
+        return ctypes.c_void_p(h if h else 1)
+
+    def center(self, i):
+        p = self.plan
+        return self.ext[i][p.H * self.plane:(p.H + p.T) * self.plane]
+
+    def halo(self, i, role, k):
+        p = self.plan
+        if role == "below":
+            return self.ext[i][(p.H - k) * self.plane:p.H * self.plane]
+        return self.ext[i][(p.H + p.T) * self.plane:(p.H + p.T + k) * self.plane]
+
+    # -- stages
+    def voxelize(self, mesh, into):
+        p = self.plan
+        need = int(self.lib.vpb_voxelize_scratch_bytes(self.n, mesh.n_tris, p.z0, p.z1))
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        self.capi.check(self.lib.vpb_voxelize_dev(_ptr(mesh.verts), mesh.n_verts, _ptr(mesh.tris), mesh.n_tris, self.n,
+                                                  self.vs, self._o(), p.z0, p.z1, _ptr(into), _ptr(self.scratch),
+                                                  self.scratch.numel(), self._stream()))
+
+    def occupancy(self, meshes, op):
+        for i, m in enumerate(meshes):
+            self.voxelize(m, self.grid_slab if i == 0 else self.grid_b)
+            if i > 0 and op != self.capi.OP_VOID:
+                self.capi.check(self.lib.vpb_csg_dev(_ptr(self.grid_slab), _ptr(self.grid_b), self.grid_slab.numel(), op,
+                                                     self._stream()))
+
+    def gather_occupancy(self):
+        if self.plan.world == 1:
+            return
+        if self.comm is not None:
+            self.comm.all_gather_bits(self)
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.grid_full, self.grid_slab.clone())
+
+    def seed(self):
+        p = self.plan
+        self.capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_full), self.n, p.z0, p.z1, _ptr(self.center(0)),
+                                                  self._stream()))
+
+    def exchange(self, k, cur):
+        """Halo exchange for step k on the current state buffer `cur` (0/1)."""
+        p = self.plan
+        if p.world == 1:
+            return
+        src = self.center(cur)
+
+        def send_view(t):
+            return src[t.src_lo * self.plane:(t.src_lo + t.count) * self.plane]
+
+        def recv_view(t):
+            if k < p.T:
+                return self.halo(cur, t.role, k)
+            return self.far[0 if t.role == "below" else 1]
+
+        sends = [(t.peer, send_view(t)) for t in p.sends(k)]
+        recvs = [(t.peer, recv_view(t)) for t in p.recvs(k)]
+        if self.comm is not None:
+            self.comm.exchange(self, k, p.sends(k), sends, p.recvs(k), recvs)
+            return
+        import torch.distributed as dist
+        ops = [dist.P2POp(dist.irecv, v, peer) for peer, v in recvs] + [dist.P2POp(dist.isend, v, peer) for peer, v in sends]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def flood(self, k, cur, last, record=False):
+        p, n = self.plan, self.n
+        mid = self.center(cur).data_ptr()
+        kb = k * self.plane * 4
+        if k < p.T or p.world == 1:
+            below, above = mid - kb, mid + kb            # contiguous extended buffer
+        else:
+            below = self.far[0].data_ptr()
+            above = self.far[1].data_ptr()
+        dst = self.center(1 - cur)
+        if record:
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.capi.check(self.lib.vpb_jfa_pass_dev(ctypes.c_void_p(below), ctypes.c_void_p(mid), ctypes.c_void_p(above),
+                                                  _ptr(dst), n, p.z0, p.z1, k, self.vs, self._o(),
+                                                  _ptr(self.grid_full) if last else None,
+                                                  _ptr(self.sdf) if last else None,
+                                                  _ptr(self.seeds) if last else None, self._stream()))
+        if record:
+            e1.record()
+            self.pass_events.append((k, e0, e1))
+
+    def run(self, meshes, op=0, sdf=True, record_passes=False):
+        self.occupancy(meshes, op)
+        self.gather_occupancy()
+        if not sdf:
+            return
+        self.seed()
+        cur = 0
+        steps = self.plan.steps()
+        for k in steps:
+            self.exchange(k, cur)
+            self.flood(k, cur, last=(k == 1), record=record_passes)
+            cur = 1 - cur
+
+    def sdf_host(self):
+        return self.sdf.cpu().numpy()
+
+
+class LocalComm:
+    """All ranks in one process / on one GPU: exchanges become device copies.  Drives the ranks in lockstep."""
+
+    def __init__(self):
+        self.ranks: List[SlabPipeline] = []
+
+    def add(self, p: SlabPipeline):
+        self.ranks.append(p)
+
+    def all_gather_bits(self, _):
+        pass  # done for everyone at once in run_all
+
+    def exchange(self, *_):
+        pass  # done for everyone at once in run_all
+
+    def run_all(self, meshes, op=0):
+        R = self.ranks
+        for p in R:
+            p.occupancy(meshes, op)
+        for p in R:
+            for q in R:
+                w = q.grid_slab.numel()
+                p.grid_full[q.plan.rank * w:(q.plan.rank + 1) * w].copy_(q.grid_slab)
+        for p in R:
+            p.seed()
+        cur = 0
+        for k in R[0].plan.steps():
+            for p in R:                                   # every receive pulls from the sender's current centre
+                for t in p.plan.recvs(k):
+                    src = R[t.peer].center(cur)[t.src_lo * p.plane:(t.src_lo + t.count) * p.plane]
+                    dst = p.halo(cur, t.role, k) if k < p.plan.T else p.far[0 if t.role == "below" else 1]
+                    dst.copy_(src)
+            for p in R:
+                p.flood(k, cur, last=(k == 1))
+            cur = 1 - cur
+        return np.concatenate([p.sdf_host() for p in R])

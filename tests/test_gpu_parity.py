@@ -184,3 +184,125 @@ def test_benchmark_mesh_1348128_faces_512(meshes, oracle, vpb):
     want, stats = oracle.voxelize(v, t, n, vs, origin, return_stats=True)
     assert stats[2] == 0 and stats[3] == 0 and stats[4] == 0
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- tiled z-march pass
+
+@pytest.mark.parametrize("mesh,n", [("torus", 64), ("bunny", 128), ("bimba", 192), ("d20", 256)])
+def test_tiled_pass_equals_gather_pass_and_oracle(mesh, n, meshes, oracle, vpb, monkeypatch):
+    """jfa_tiled.cu (z-march, packed f32x2 math) against the straightforward gather kernel and the oracle,
+    including the nearest-seed indices (tie-breaking)."""
+    v, t = meshes[mesh]
+    origin, vs = oracle.frame(v, n)
+    words = oracle.voxelize(v, t, n, vs, origin)
+    sdf_t, seeds_t = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_KERNEL", "gather")
+    sdf_g, seeds_g = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_KERNEL")
+    assert np.array_equal(sdf_t.view(np.uint32), sdf_g.view(np.uint32))
+    assert np.array_equal(seeds_t, seeds_g)
+    if n <= 192:
+        osdf, oseeds = oracle.jfa(words, n, vs, origin, want_seeds=True)
+        assert np.array_equal(sdf_t.view(np.uint32), osdf.view(np.uint32))
+        assert np.array_equal(seeds_t, _public_seeds(oseeds, n))
+
+
+def test_tiled_pass_on_random_dense_ties(oracle, vpb):
+    """Random occupancy at N=64/128: every pass is full of exact distance ties; scan order must decide identically."""
+    for n, seed in [(64, 1), (128, 2)]:
+        rng = np.random.default_rng(seed)
+        nw = n ** 3 // 32
+        words = rng.integers(0, 2 ** 32, nw, dtype=np.uint32) & rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
+        sparse = np.zeros(nw, np.uint32)
+        sparse[rng.integers(0, nw, 40)] = 1 << 7          # a few isolated seeds: exercises the sparse early passes
+        for w in (words, sparse):
+            o = np.array([-3.25, 0.5, 11.0], np.float32)
+            sdf, seeds = vpb.jfa_host(w, n, 0.0371, o, want_seeds=True)
+            osdf, oseeds = oracle.jfa(w, n, 0.0371, o, want_seeds=True)
+            assert np.array_equal(sdf.view(np.uint32), osdf.view(np.uint32))
+            assert np.array_equal(seeds, _public_seeds(oseeds, n))
+
+
+# ---------------------------------------------------------------------------------------------- device-resident + slabs
+
+def test_device_pipeline_matches_host_pipeline(golden, meshes, oracle, vpb):
+    import torch
+    from cuda_mesh_voxelization_b200.device import DeviceMesh, DevicePipeline
+    rec = golden["bimba_union_bunny_n256"]
+    n = rec["n"]
+    origin, vs = _frame(oracle, meshes, rec["meshes"], n)
+    pipe = DevicePipeline(n, vs, origin, want_seeds=True)
+    dm = [DeviceMesh(*meshes[m], "cuda:0") for m in rec["meshes"]]
+    pipe.run(dm, op=rec["op"], sdf=True, record_passes=True)
+    torch.cuda.synchronize()
+    assert f"{oracle.fnv(pipe.words_host()):016x}" == rec["result"]["fnv"]
+    assert f"{oracle.fnv(pipe.sdf_host()):016x}" == rec["sdf"]["fnv"]
+    assert len(pipe.pass_events) == 8 and all(a.elapsed_time(b) > 0 for _, a, b in pipe.pass_events)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_z_slabs_are_bit_identical_to_one_gpu(world, meshes, oracle, vpb):
+    """The multi-GPU code path (slab voxelization, halo / far-slab sources, slab-local marches) emulated with all
+    slabs on one GPU: the concatenated slab outputs must equal the single-GPU result and the oracle."""
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    from cuda_mesh_voxelization_b200.multi import LocalComm, SlabPipeline
+    n = 128
+    names = ["bimba", "bunny"]
+    origin, vs = _frame(oracle, meshes, names, n)
+    dm = [DeviceMesh(*meshes[m], "cuda:0") for m in names]
+    comm = LocalComm()
+    for r in range(world):
+        comm.add(SlabPipeline(n, vs, origin, r, world, comm=comm))
+    sdf = comm.run_all(dm, op=capi.OP_DIFFERENCE)
+    torch.cuda.synchronize()
+    words = np.concatenate([p.grid_slab.cpu().numpy().view(np.uint32) for p in comm.ranks])
+    want = oracle.csg(oracle.voxelize(*meshes["bimba"], n, vs, origin), oracle.voxelize(*meshes["bunny"], n, vs, origin), n, 3)
+    assert np.array_equal(words, want)
+    assert np.array_equal(sdf.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
+
+
+def test_full_size_1024_properties(meshes, oracle, vpb):
+    """BASELINE's metric configuration (1024^3, 1 348 128 faces ∪ bimba): occupancy bit-exact against the oracle;
+    the SDF (too large for the CPU oracle) through size-independent properties."""
+    import torch
+    from cuda_mesh_voxelization_b200 import capi, meshgen
+    from cuda_mesh_voxelization_b200.device import DeviceMesh, DevicePipeline
+    n = 1024
+    bunny = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
+    ms = [bunny, meshes["bimba"]]
+    origin, vs = oracle.frame(np.concatenate([m[0] for m in ms]), n)
+    pipe = DevicePipeline(n, vs, origin, want_seeds=True)
+    pipe.run([DeviceMesh(*m, "cuda:0") for m in ms], op=capi.OP_UNION, sdf=True)
+    torch.cuda.synchronize()
+    words = pipe.words_host()
+    want = oracle.csg(oracle.voxelize(*ms[0], n, vs, origin), oracle.voxelize(*ms[1], n, vs, origin), n, 1)
+    assert np.array_equal(words, want)
+    sdf, seeds, bits = pipe.sdf, pipe.seeds, pipe.grid_a
+    vox = n ** 3
+    # (1) sign == occupancy everywhere; (2) zero set == seed shell; (3) every voxel found a seed
+    idx = torch.arange(vox, device="cuda", dtype=torch.int64)
+    inside = ((bits[idx >> 5] >> (idx & 31).to(torch.int32)) & 1).bool()
+    del idx
+    assert bool(torch.all(torch.signbit(sdf) == ~inside))
+    shell = torch.from_numpy(oracle.seed_shell(want, n).view(np.int32)).cuda()
+    n_seeds = int(oracle.popcount(shell.cpu().numpy().view(np.uint32)))
+    assert int((sdf == 0).sum()) == n_seeds
+    assert bool(torch.isfinite(sdf).all())
+    # (4) self-consistency: |sdf| is exactly the reference distance formula applied to the returned seed
+    i = torch.arange(n, device="cuda", dtype=torch.float32)
+    tab = [torch.tensor(float(origin[a]), device="cuda") + i * torch.tensor(float(vs), device="cuda") for a in range(3)]
+    step = 64
+    for z0 in range(0, n, step):                                  # chunked to bound memory
+        sl = slice(z0 * n * n, (z0 + step) * n * n)
+        s = seeds[sl].to(torch.int64)
+        sx, sy, sz = s & 1023, (s >> 10) & 1023, (s >> 20) & 1023
+        lin = torch.arange(z0 * n * n, (z0 + step) * n * n, device="cuda", dtype=torch.int64)
+        qx, qy, qz = lin % n, (lin // n) % n, lin // (n * n)
+        dx, dy, dz = tab[0][sx] - tab[0][qx], tab[1][sy] - tab[1][qy], tab[2][sz] - tab[2][qz]
+        d = (dx * dx + dy * dy) + dz * dz
+        assert bool(torch.all(d == sdf[sl].abs()))
+        # (5) every returned seed is a shell voxel
+        sl_lin = sx + n * (sy + n * sz)
+        assert bool(torch.all(((shell[sl_lin >> 5] >> (sl_lin & 31).to(torch.int32)) & 1) == 1))
