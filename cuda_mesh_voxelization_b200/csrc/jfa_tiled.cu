@@ -14,7 +14,7 @@
 //   * all float work is done two voxels at a time with the sm_100 packed-FP32 instructions (FADD2 / FFMA2:
 //     individually rounded lanes, bit-identical to scalar code — see sq2() for the one ptxas pitfall);
 //   * when the y-lattice has <= 8 points (large k) a CTA takes whole lattice columns of several y-residues instead
-//     of a tile with halo rows, and out-of-grid planes are never staged.
+//     of a tile with halo rows (plus skipping of candidates no lane of the warp has a seed for).
 // Candidate order (dz outer, dy, dx inner, own value first, strict <) and every rounding are the reference's
 // (vplib/src/jfa/sequential.cpp:84-113, jfa/jfa.h:19-20).
 #include "common.cuh"
@@ -44,8 +44,8 @@ struct Tile {
     static constexpr int OFF_FX = 3 * MAXN;
     static constexpr int OFF_FY = OFF_FX + PLANE;
     static constexpr int OFF_FZ = OFF_FY + PLANE;
-    static constexpr int OFF_PS = OFF_FZ + PLANE;    // ring of 3 packed planes
-    static constexpr int WORDS = OFF_PS + 3 * PLANE;
+    static constexpr int OFF_PS = OFF_FZ + PLANE;    // ring of 4 packed planes (3 live; 4 keeps the phase a power of 2)
+    static constexpr int WORDS = OFF_PS + 4 * PLANE;
     static constexpr size_t BYTES = (size_t)WORDS * 4;
 };
 
@@ -86,8 +86,10 @@ struct Cache {
     uint32_t any[2];   // SPARSE: bit c set if any lane of the warp has a valid candidate c in that plane
 };
 
-template <int SS, bool FINAL, bool SPARSE>
+// COL: column mode (y lattice <= 8 points, the early sparse passes): runtime row offsets + empty-candidate skipping.
+template <int SS, bool FINAL, bool COL>
 struct March {
+    static constexpr bool SPARSE = COL;
     using TL = Tile<SS>;
     static constexpr bool ALIGNED = (SS % 2) == 0;
 
@@ -137,14 +139,19 @@ struct March {
         }
     }
 
+    // shared-memory word offset of candidate (dy, dx) relative to the thread base (tile mode: compile-time)
+    static __device__ __forceinline__ int cand_off(const int (&tbr)[3], int cc) {
+        return (COL ? tbr[cc / 3] : (cc / 3) * TL::W) + (cc % 3) * SS;
+    }
+
     // candidate cc of the staged (newest) plane -> cache slot SLOT
     template <int SLOT>
-    static __device__ __forceinline__ bool convert(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
-                                                   float2 nz, int cc) {
-        const int off = tb[cc / 3] + (cc % 3) * SS;
-        const float2 sx = ld2(sm + TL::OFF_FX + off, ALIGNED);
-        const float2 sy = ld2(sm + TL::OFF_FY + off, ALIGNED);
-        const float2 sz = ld2(sm + TL::OFF_FZ + off, ALIGNED);
+    static __device__ __forceinline__ bool convert(Cache& c, const float* smt, const int (&tbr)[3], float2 nqx,
+                                                   float2 nqy, float2 nz, int cc) {
+        const int off = cand_off(tbr, cc);
+        const float2 sx = ld2(smt + TL::OFF_FX + off, ALIGNED);
+        const float2 sy = ld2(smt + TL::OFF_FY + off, ALIGNED);
+        const float2 sz = ld2(smt + TL::OFF_FZ + off, ALIGNED);
         const float2 ddx = __fadd2_rn(sx, nqx);          // seed - voxel (the exact negation is folded into nq*)
         const float2 ddy = __fadd2_rn(sy, nqy);
         c.xy[SLOT][cc] = __fadd2_rn(sq2(ddx, nz), sq2(ddy, nz));
@@ -153,25 +160,14 @@ struct March {
         return __any_sync(0xffffffffu, (sz.x != INFINITY) || (sz.y != INFINITY));
     }
 
-    // a plane outside the grid: nothing was staged, every candidate is "no seed"
-    template <int SLOT>
-    static __device__ __forceinline__ void invalidate(Cache& c) {
-#pragma unroll
-        for (int cc = 0; cc < 9; ++cc) {
-            c.xy[SLOT][cc] = make_float2(0.0f, 0.0f);
-            c.fz[SLOT][cc] = make_float2(INFINITY, INFINITY);
-        }
-        c.any[SLOT] = 0;
-    }
-
     // priming: the first two planes of a march only fill the cache
     template <int SLOT>
-    static __device__ __forceinline__ void consume(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
-                                                   float2 nz) {
+    static __device__ __forceinline__ void consume(Cache& c, const float* smt, const int (&tbr)[3], float2 nqx,
+                                                   float2 nqy, float2 nz) {
         uint32_t any = 0;
 #pragma unroll
         for (int cc = 0; cc < 9; ++cc)
-            if (convert<SLOT>(c, sm, tb, nqx, nqy, nz, cc)) any |= 1u << cc;
+            if (convert<SLOT>(c, smt, tbr, nqx, nqy, nz, cc)) any |= 1u << cc;
         c.any[SLOT] = any;
     }
 
@@ -186,43 +182,42 @@ struct March {
         best.y = fminf(best.y, d.y);
     }
 
-    // One output plane.  Cache slot RS holds plane z-k on entry and receives plane z+k; slot 1-RS holds plane z.
-    // ring_p/q/r: word offsets of the three planes inside the packed ring.
-    template <int RS>
-    static __device__ __forceinline__ void emit(Cache& c, const float* sm, const int (&tb)[3], float2 nqx, float2 nqy,
-                                                float2 nz, float nqz_s, int ring_p, int ring_q, int ring_r, bool r_ok,
-                                                const PassArgs& a, int zl, int gy, int xs, int lane) {
-        constexpr int QS = 1 - RS;
+    // One output plane.  PH = (p + 1) & 3 is the phase of the march: the newest plane p sits in ring slot PH and goes
+    // to cache slot PH & 1 (replacing plane p-2, which is scanned first); plane p-1 is in ring slot PH-1, cache slot
+    // 1 - (PH & 1).  `smt` is the shared buffer already offset by the thread base (tile mode) so that every candidate
+    // address, and every "winner" code, is an immediate.
+    template <int PH>
+    static __device__ __forceinline__ void emit(Cache& c, const float* smt, const int (&tbr)[3], float2 nqx, float2 nqy,
+                                                float2 nz, float nqz_s, const PassArgs& a, int zl, int gy, int xs,
+                                                int lane) {
+        constexpr int RS = PH & 1, QS = 1 - RS;
+        constexpr int RING_R = PH * TL::PLANE, RING_Q = ((PH + 3) & 3) * TL::PLANE, RING_P = ((PH + 2) & 3) * TL::PLANE;
         const float2 nqz = make_float2(nqz_s, nqz_s);
         // own value first (sequential.cpp:83: bestDistance = sdf(voxel)); +INF while the voxel has no seed
         const float2 dz0 = __fadd2_rn(c.fz[QS][4], nqz);
         float2 best = __fadd2_rn(c.xy[QS][4], sq2(dz0, nz));
-        int ia = ring_q + tb[1] + SS, ib = ia;
+        int ia = RING_Q + cand_off(tbr, 4), ib = ia;
 #pragma unroll
         for (int cc = 0; cc < 9; ++cc) {                       // plane z-k
             if (SPARSE && !((c.any[RS] >> cc) & 1u)) continue;
-            eval<RS>(c, cc, nqz, nz, ring_p + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
+            eval<RS>(c, cc, nqz, nz, RING_P + cand_off(tbr, cc), best, ia, ib);
         }
 #pragma unroll
         for (int cc = 0; cc < 9; ++cc) {                       // plane z, own voxel skipped
             if (cc == 4) continue;
             if (SPARSE && !((c.any[QS] >> cc) & 1u)) continue;
-            eval<QS>(c, cc, nqz, nz, ring_q + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
+            eval<QS>(c, cc, nqz, nz, RING_Q + cand_off(tbr, cc), best, ia, ib);
         }
-        if (r_ok) {
-            uint32_t any = 0;
+        uint32_t any = 0;
 #pragma unroll
-            for (int cc = 0; cc < 9; ++cc) {                   // plane z+k: convert into the freed slot, then scan
-                if (convert<RS>(c, sm, tb, nqx, nqy, nz, cc)) {
-                    any |= 1u << cc;
-                    eval<RS>(c, cc, nqz, nz, ring_r + tb[cc / 3] + (cc % 3) * SS, best, ia, ib);
-                }
+        for (int cc = 0; cc < 9; ++cc) {                       // plane z+k: convert into the freed slot, then scan
+            if (convert<RS>(c, smt, tbr, nqx, nqy, nz, cc)) {
+                any |= 1u << cc;
+                eval<RS>(c, cc, nqz, nz, RING_R + cand_off(tbr, cc), best, ia, ib);
             }
-            c.any[RS] = any;
-        } else {
-            invalidate<RS>(c);
         }
-        const uint32_t* ps = reinterpret_cast<const uint32_t*>(sm + TL::OFF_PS);
+        c.any[RS] = any;
+        const uint32_t* ps = reinterpret_cast<const uint32_t*>(smt + TL::OFF_PS);
         const uint32_t sa = ps[ia], sb = ps[ib + 1];
         const int n = (int)a.f.n;
         const size_t v = ((size_t)zl * n + gy) * n + xs + 2 * lane;
@@ -241,7 +236,6 @@ struct March {
         extern __shared__ float sm[];
         const int n = (int)a.f.n, k = a.k;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const bool col = a.column_mode != 0;
         // world-position tables p(i) = origin + float(i) * voxelSize (sequential.cpp:32-34,78-80)
         for (int i = threadIdx.x; i < n; i += THREADS) {
             const float t = __fmul_rn((float)i, a.f.vs);
@@ -259,7 +253,7 @@ struct March {
         // own output row of this warp, staged row index of the rows it reads for dy = -1, 0, +1
         int gy, row[3], own_row;
         bool row_ok;
-        if (!col) {
+        if (!COL) {
             const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
             gy = ry + (ty * TW + warp) * k;
             row_ok = gy < n;
@@ -290,7 +284,7 @@ struct March {
             st.halo_off[v] = -1;
             st.halo_sm[v] = -1;
             const int h = (int)threadIdx.x + THREADS * v;
-            if (!col && h < 2 * TL::W) {
+            if (!COL && h < 2 * TL::W) {
                 const int top = h >= TL::W;                     // 0: staged row 0, 1: staged row 9
                 const int i = h - top * TL::W;
                 const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
@@ -300,13 +294,14 @@ struct March {
                 if (hy >= 0 && hy < n && gx >= 0 && gx < n) st.halo_off[v] = hy * n + gx;
             }
         }
-        if (col) {  // the dummy row never changes: "no seed" in the float buffers and in all three ring slots
+        if (COL) {  // the dummy row never changes: "no seed" in the float buffers and in every ring slot
             uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS);
             for (int i = threadIdx.x; i < TL::W; i += THREADS) {
                 sm[TL::OFF_FX + TW * TL::W + i] = 0.0f;
                 sm[TL::OFF_FY + TW * TL::W + i] = 0.0f;
                 sm[TL::OFF_FZ + TW * TL::W + i] = INFINITY;
-                ps[TW * TL::W + i] = 0u; ps[TL::PLANE + TW * TL::W + i] = 0u; ps[2 * TL::PLANE + TW * TL::W + i] = 0u;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) ps[r * TL::PLANE + TW * TL::W + i] = 0u;
             }
         }
         const size_t plane_sz = (size_t)n * n;
@@ -317,43 +312,48 @@ struct March {
         const float qy_s = row_ok ? lut[MAXN + gy] : 0.0f;
         const float2 nqy = make_float2(-qy_s, -qy_s);
         const float2 nz = make_float2(a.neg_zero, a.neg_zero);
-        const int tb[3] = {row[0] * TL::W + 2 * lane, row[1] * TL::W + 2 * lane, row[2] * TL::W + 2 * lane};
+        // tile mode: candidate rows are warp, warp+1, warp+2 -> fold the thread base into the pointer, offsets become
+        // immediates.  column mode: per-thread row offsets (dummy row for out-of-lattice neighbours).
+        const float* smt = COL ? sm : sm + (warp * TL::W + 2 * lane);
+        const int tbr[3] = {row[0] * TL::W + 2 * lane, row[1] * TL::W + 2 * lane, row[2] * TL::W + 2 * lane};
 
         Cache c;
         uint32_t own[TL::U], halo[TL::HV];
-        // plane p (p = -1 .. steps) of the march: slab-local z = zl0 + p*k
-        auto plane_ptr = [&](int p, bool& ok) -> const uint32_t* {
+        // plane p (p = -1 .. steps) of the march: slab-local z = zl0 + p*k.  Planes outside the grid are staged as
+        // all-"no seed" (zeros) so that the steady-state code has no special cases.
+        auto fetch = [&](int p) {
             const int zl = zl0 + p * k;
             const int gz = zl + (int)a.z0;
-            ok = gz >= 0 && gz < n;
-            if (a.contiguous) return a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz;
-            return (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;   // steps == 1 here
+            const uint32_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
+                                              : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
+            if (gz >= 0 && gz < n) {
+                prefetch(own, halo, st, pp, COL);
+            } else {
+#pragma unroll
+                for (int u = 0; u < TL::U; ++u) own[u] = 0u;
+#pragma unroll
+                for (int v = 0; v < TL::HV; ++v) halo[v] = 0u;
+            }
         };
-        bool ok_next;
-        const uint32_t* pp = plane_ptr(-1, ok_next);
-        if (ok_next) prefetch(own, halo, st, pp, col);
-        int ring_p = 0, ring_q = 0, ring_r = 0;                 // ring slot (in words) of planes p-2, p-1, p
+        fetch(-1);
 #pragma unroll 1
         for (int p = -1; p <= steps; ++p) {
-            const bool ok = ok_next;
-            ring_p = ring_q; ring_q = ring_r;
-            ring_r = ((p + 1) % 3) * TL::PLANE;
-            if (ok) stage(own, halo, st, sm, (p + 1) % 3, col, lane);
+            const int ph = (p + 1) & 3;
+            stage(own, halo, st, sm, ph, COL, lane);
             __syncthreads();
-            if (p < steps) {
-                pp = plane_ptr(p + 1, ok_next);
-                if (ok_next) prefetch(own, halo, st, pp, col);
-            }
+            if (p < steps) fetch(p + 1);
             if (row_ok) {
                 if (p < 1) {
-                    if (p == -1) { if (ok) consume<0>(c, sm, tb, nqx, nqy, nz); else invalidate<0>(c); }
-                    else         { if (ok) consume<1>(c, sm, tb, nqx, nqy, nz); else invalidate<1>(c); }
+                    if (p == -1) consume<0>(c, smt, tbr, nqx, nqy, nz); else consume<1>(c, smt, tbr, nqx, nqy, nz);
                 } else {
                     const int zl = zl0 + (p - 1) * k;
                     const float nqz = -lut[2 * MAXN + zl + (int)a.z0];
-                    // plane q lives in cache slot (q+1)&1: the newest plane p replaces plane p-2
-                    if ((p + 1) & 1) emit<1>(c, sm, tb, nqx, nqy, nz, nqz, ring_p, ring_q, ring_r, ok, a, zl, gy, xs, lane);
-                    else emit<0>(c, sm, tb, nqx, nqy, nz, nqz, ring_p, ring_q, ring_r, ok, a, zl, gy, xs, lane);
+                    switch (ph) {
+                        case 0: emit<0>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
+                        case 1: emit<1>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
+                        case 2: emit<2>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
+                        default: emit<3>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
+                    }
                 }
             }
             __syncthreads();
@@ -361,27 +361,26 @@ struct March {
     }
 };
 
-template <int SS, bool FINAL, bool SPARSE>
-__global__ void __launch_bounds__(THREADS, 2) jfa_pass_march(const PassArgs a) { March<SS, FINAL, SPARSE>::run(a); }
+template <int SS, bool FINAL, bool COL>
+__global__ void __launch_bounds__(THREADS, 2) jfa_pass_march(const PassArgs a) { March<SS, FINAL, COL>::run(a); }
 
-template <int SS, bool FINAL, bool SPARSE>
+template <int SS, bool FINAL, bool COL>
 int launch_one(const PassArgs& a, dim3 grid, cudaStream_t st) {
     using TL = Tile<SS>;
     static bool configured = false;
     if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_march<SS, FINAL, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
+        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_march<SS, FINAL, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
         configured = true;
     }
-    jfa_pass_march<SS, FINAL, SPARSE><<<grid, THREADS, TL::BYTES, st>>>(a);
+    jfa_pass_march<SS, FINAL, COL><<<grid, THREADS, TL::BYTES, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;
 }
 
 template <int SS>
-int launch_ss(const PassArgs& a, dim3 grid, bool fin, bool sparse, cudaStream_t st) {
-    if (fin) return launch_one<SS, true, false>(a, grid, st);
-    if (sparse) return launch_one<SS, false, true>(a, grid, st);
-    return launch_one<SS, false, false>(a, grid, st);
+int launch_ss(const PassArgs& a, dim3 grid, bool fin, cudaStream_t st) {
+    if (a.column_mode) return fin ? launch_one<SS, true, true>(a, grid, st) : launch_one<SS, false, true>(a, grid, st);
+    return fin ? launch_one<SS, true, false>(a, grid, st) : launch_one<SS, false, false>(a, grid, st);
 }
 
 }  // namespace
@@ -422,15 +421,14 @@ int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint
     dim3 grid(n / SEG, grid_y, res_z * a.segs_z);
     VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
     const bool fin = sdf != nullptr;
-    const bool sparse = !fin && k >= n / 8;                     // the first passes see few seeds: skip empty candidates
     switch (k >= 64 ? 64 : (int)k) {
-        case 64: return launch_ss<64>(a, grid, fin, sparse, st);
-        case 32: return launch_ss<32>(a, grid, fin, sparse, st);
-        case 16: return launch_ss<16>(a, grid, fin, sparse, st);
-        case 8: return launch_ss<8>(a, grid, fin, sparse, st);
-        case 4: return launch_ss<4>(a, grid, fin, sparse, st);
-        case 2: return launch_ss<2>(a, grid, fin, sparse, st);
-        default: return launch_ss<1>(a, grid, fin, sparse, st);
+        case 64: return launch_ss<64>(a, grid, fin, st);
+        case 32: return launch_ss<32>(a, grid, fin, st);
+        case 16: return launch_ss<16>(a, grid, fin, st);
+        case 8: return launch_ss<8>(a, grid, fin, st);
+        case 4: return launch_ss<4>(a, grid, fin, st);
+        case 2: return launch_ss<2>(a, grid, fin, st);
+        default: return launch_ss<1>(a, grid, fin, st);
     }
 }
 
