@@ -35,13 +35,16 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu into objects (in parallel) and link libvpb200.so next to this file."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Compile every .cu into objects (in parallel) and link libvpb200.so next to this file.
+    `extra_flags`/`out` build an experimental variant (tools/variants.py) without touching the product library."""
+    if out is None and os.environ.get("VPB_LIB"):
+        return os.environ["VPB_LIB"]
+    if out is None and not force and not _stale():
         return LIB
     nvcc = _nvcc()
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build") if out is None else out + ".obj"
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
@@ -51,21 +54,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            print(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            print(log)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    link = [nvcc, "-ccbin", host_cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
+            raise RuntimeError(f"nvcc failed on {s}:\n{log}")
+    target = LIB if out is None else out
+    link = [nvcc, "-ccbin", host_cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -62,7 +62,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build() if build_if_missing else _build.LIB
+    path = _build.build() if build_if_missing else (os.environ.get("VPB_LIB") or _build.LIB)
     if not os.path.exists(path):
         raise VpbError(f"{path} is missing: the CUDA extension was not built (no CPU fallback exists)")
     lib = ctypes.CDLL(path)

@@ -173,11 +173,42 @@ jfa_finalize(const uint32_t* __restrict__ state, Frame f, uint32_t z0, uint64_t 
     }
 }
 
+// px | py | pz tables in global memory for the tiled pass (3 * MAX_N floats, same expression as fill_tables)
+__global__ void jfa_lut_kernel(Frame f, float* __restrict__ lut) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MAX_N) return;
+    const float t = __fmul_rn((float)i, f.vs);
+    lut[i] = __fadd_rn(f.ox, t);
+    lut[MAX_N + i] = __fadd_rn(f.oy, t);
+    lut[2 * MAX_N + i] = __fadd_rn(f.oz, t);
+}
+
 unsigned grid_for(uint64_t items) {
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, (uint64_t)num_sms() * 16));
 }
 
 }  // namespace
+
+// One 12 KB device buffer per process (the library serves one caller thread / one frame at a time, like vplib).
+// Rebuilt on every pass launch: 3 us, stream-ordered before the pass that reads it.
+const float* jfa_lut_launch(const Frame& f, cudaStream_t st) {
+    static float* lut = nullptr;
+    static int lut_device = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (!lut || lut_device != dev) {
+        if (cudaMalloc(&lut, 3 * MAX_N * sizeof(float)) != cudaSuccess) {
+            set_error("jfa: cannot allocate the position tables");
+            lut = nullptr;
+            return nullptr;
+        }
+        lut_device = dev;
+    }
+    jfa_lut_kernel<<<MAX_N / 256, 256, 0, st>>>(f, lut);
+    count_launch();
+    if (cudaPeekAtLastError() != cudaSuccess) { set_error("jfa_lut_kernel launch failed"); return nullptr; }
+    return lut;
+}
 
 int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st) {
     VPB_REQUIRE(words_full && state, "jfa_seed: null buffer");

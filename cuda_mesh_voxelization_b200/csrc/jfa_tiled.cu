@@ -21,11 +21,20 @@
 
 namespace vpb {
 
+const float* jfa_lut_launch(const Frame& f, cudaStream_t st);   // jfa.cu
+
 int jfa_pass_gather_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
                            const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
                            float* sdf, uint32_t* seeds, cudaStream_t st);
 
 namespace {
+
+#ifndef VPB_MARCH_MINBLOCKS
+#define VPB_MARCH_MINBLOCKS 2
+#endif
+#ifndef VPB_PRED_MOV
+#define VPB_PRED_MOV 0
+#endif
 
 constexpr int TW = 8;            // warps per CTA == output rows per CTA
 constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
@@ -64,6 +73,7 @@ struct PassArgs {
     int column_mode;          // y lattice has <= 8 points: CTA = whole columns of `8 / lp` y-residues
     int lp, ly;               // column mode: padded (power of two) and true lattice length in y
     float neg_zero;           // -0.0f, deliberately a RUNTIME value: see sq2()
+    const float* glut;        // px | py | pz world-position tables in global memory, 3 * MAXN floats (jfa_lut_kernel)
 };
 
 __device__ __forceinline__ float2 ld2(const float* p, bool aligned) {
@@ -116,26 +126,51 @@ struct March {
         }
     }
 
-    static __device__ __forceinline__ void put(float* sm, uint32_t* ps, int e, uint32_t s) {
-        const char* lut = reinterpret_cast<const char*>(sm + TL::OFF_LUT);
-        sm[TL::OFF_FX + e] = *reinterpret_cast<const float*>(lut + (s & 0xFFCu));
-        sm[TL::OFF_FY + e] = *reinterpret_cast<const float*>(lut + 4 * MAXN + ((s >> 10) & 0xFFCu));
-        const float z = *reinterpret_cast<const float*>(lut + 8 * MAXN + ((s >> 20) & 0xFFCu));
+    static __device__ __forceinline__ float table(const float* sm, const float*, int axis, uint32_t byte_off) {
+        return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(sm + TL::OFF_LUT + axis * MAXN) + byte_off);
+    }
+
+    static __device__ __forceinline__ void put(float* sm, const float* glut, uint32_t* ps, int e, uint32_t s) {
+        sm[TL::OFF_FX + e] = table(sm, glut, 0, s & 0xFFCu);
+        sm[TL::OFF_FY + e] = table(sm, glut, 1, (s >> 10) & 0xFFCu);
+        const float z = table(sm, glut, 2, (s >> 20) & 0xFFCu);
         sm[TL::OFF_FZ + e] = s ? z : INFINITY;   // one infinite coordinate makes the whole distance +INF
         ps[e] = s;
     }
 
-    // registers -> shared: world coordinates of the seeds + packed ring slot
-    static __device__ __forceinline__ void stage(const uint32_t (&own)[TL::U], const uint32_t (&halo)[TL::HV],
-                                                 const Stager& s, float* sm, int ring_slot, bool column_mode, int lane) {
-        uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS) + ring_slot * TL::PLANE;
+    static __device__ __forceinline__ void put_invalid(float* sm, int e) {
+        uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS);
+        sm[TL::OFF_FX + e] = 0.0f;
+        sm[TL::OFF_FY + e] = 0.0f;
+        sm[TL::OFF_FZ + e] = INFINITY;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ps[r * TL::PLANE + e] = 0u;
+    }
+
+    // once per CTA: the staged entries that lie outside the grid in x or y never change
+    static __device__ __forceinline__ void init_invalid(const Stager& s, float* sm, bool column_mode, int lane) {
 #pragma unroll
         for (int u = 0; u < TL::U; ++u)
-            if (TL::W % 32 == 0 || lane + 32 * u < TL::W) put(sm, ps, s.own_sm + 32 * u, own[u]);
+            if (s.own_off[u] < 0 && (TL::W % 32 == 0 || lane + 32 * u < TL::W)) put_invalid(sm, s.own_sm + 32 * u);
         if (!column_mode) {
 #pragma unroll
             for (int v = 0; v < TL::HV; ++v)
-                if (s.halo_sm[v] >= 0) put(sm, ps, s.halo_sm[v], halo[v]);
+                if (s.halo_off[v] < 0 && s.halo_sm[v] >= 0) put_invalid(sm, s.halo_sm[v]);
+        }
+    }
+
+    // registers -> shared: world coordinates of the seeds + packed ring slot
+    static __device__ __forceinline__ void stage(const uint32_t (&own)[TL::U], const uint32_t (&halo)[TL::HV],
+                                                 const Stager& s, float* sm, const float* glut, int ring_slot, bool column_mode, int lane) {
+        uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS) + ring_slot * TL::PLANE;
+        // entries outside the grid in x/y are "no seed" for every plane: written once by init_invalid()
+#pragma unroll
+        for (int u = 0; u < TL::U; ++u)
+            if (s.own_off[u] >= 0) put(sm, glut, ps, s.own_sm + 32 * u, own[u]);
+        if (!column_mode) {
+#pragma unroll
+            for (int v = 0; v < TL::HV; ++v)
+                if (s.halo_off[v] >= 0) put(sm, glut, ps, s.halo_sm[v], halo[v]);
         }
     }
 
@@ -176,8 +211,14 @@ struct March {
                                                 int& ia, int& ib) {
         const float2 ddz = __fadd2_rn(c.fz[SLOT][cc], nqz);
         const float2 d = __fadd2_rn(c.xy[SLOT][cc], sq2(ddz, nz));   // ((dx*dx)+(dy*dy)) + (dz*dz)
+#if VPB_PRED_MOV
+        // predicated immediate moves: keeps the index update off the (saturated) ALU pipe when ptxas picks IMAD.MOV
+        asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p mov.u32 %0, %3; }" : "+r"(ia) : "f"(d.x), "f"(best.x), "r"(code));
+        asm("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p mov.u32 %0, %3; }" : "+r"(ib) : "f"(d.y), "f"(best.y), "r"(code));
+#else
         if (d.x < best.x) ia = code;                                 // strict <: the earlier candidate keeps ties
         if (d.y < best.y) ib = code;
+#endif
         best.x = fminf(best.x, d.x);
         best.y = fminf(best.y, d.y);
     }
@@ -188,8 +229,8 @@ struct March {
     // address, and every "winner" code, is an immediate.
     template <int PH>
     static __device__ __forceinline__ void emit(Cache& c, const float* smt, const int (&tbr)[3], float2 nqx, float2 nqy,
-                                                float2 nz, float nqz_s, const PassArgs& a, int zl, int gy, int xs,
-                                                int lane) {
+                                                float2 nz, float nqz_s, bool skip_r, const PassArgs& a, int zl, int gy,
+                                                int xs, int lane) {
         constexpr int RS = PH & 1, QS = 1 - RS;
         constexpr int RING_R = PH * TL::PLANE, RING_Q = ((PH + 3) & 3) * TL::PLANE, RING_P = ((PH + 2) & 3) * TL::PLANE;
         const float2 nqz = make_float2(nqz_s, nqz_s);
@@ -209,11 +250,13 @@ struct March {
             eval<QS>(c, cc, nqz, nz, RING_Q + cand_off(tbr, cc), best, ia, ib);
         }
         uint32_t any = 0;
+        if (!(COL && skip_r)) {
 #pragma unroll
-        for (int cc = 0; cc < 9; ++cc) {                       // plane z+k: convert into the freed slot, then scan
-            if (convert<RS>(c, smt, tbr, nqx, nqy, nz, cc)) {
-                any |= 1u << cc;
-                eval<RS>(c, cc, nqz, nz, RING_R + cand_off(tbr, cc), best, ia, ib);
+            for (int cc = 0; cc < 9; ++cc) {                   // plane z+k: convert into the freed slot, then scan
+                if (convert<RS>(c, smt, tbr, nqx, nqy, nz, cc)) {
+                    any |= 1u << cc;
+                    eval<RS>(c, cc, nqz, nz, RING_R + cand_off(tbr, cc), best, ia, ib);
+                }
             }
         }
         c.any[RS] = any;
@@ -236,12 +279,13 @@ struct March {
         extern __shared__ float sm[];
         const int n = (int)a.f.n, k = a.k;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        // world-position tables p(i) = origin + float(i) * voxelSize (sequential.cpp:32-34,78-80)
-        for (int i = threadIdx.x; i < n; i += THREADS) {
-            const float t = __fmul_rn((float)i, a.f.vs);
-            sm[TL::OFF_LUT + i] = __fadd_rn(a.f.ox, t);
-            sm[TL::OFF_LUT + MAXN + i] = __fadd_rn(a.f.oy, t);
-            sm[TL::OFF_LUT + 2 * MAXN + i] = __fadd_rn(a.f.oz, t);
+        // world-position tables p(i) = origin + float(i) * voxelSize (sequential.cpp:32-34,78-80), built once per
+        // pass by jfa_lut_kernel (measured: recomputing 3N entries per CTA or reading them from L1 per lookup are
+        // both slower for the short-lived CTAs of the large-k passes); each CTA copies them with 3 x 128-bit loads
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(a.glut);
+            float4* s4 = reinterpret_cast<float4*>(sm + TL::OFF_LUT);
+            for (int i = threadIdx.x; i < 3 * MAXN / 4; i += THREADS) s4[i] = __ldg(g4 + i);
         }
         // ---- tile coordinates -------------------------------------------------------------------------------
         const int xs = blockIdx.x * SEG;
@@ -294,16 +338,9 @@ struct March {
                 if (hy >= 0 && hy < n && gx >= 0 && gx < n) st.halo_off[v] = hy * n + gx;
             }
         }
-        if (COL) {  // the dummy row never changes: "no seed" in the float buffers and in every ring slot
-            uint32_t* ps = reinterpret_cast<uint32_t*>(sm + TL::OFF_PS);
-            for (int i = threadIdx.x; i < TL::W; i += THREADS) {
-                sm[TL::OFF_FX + TW * TL::W + i] = 0.0f;
-                sm[TL::OFF_FY + TW * TL::W + i] = 0.0f;
-                sm[TL::OFF_FZ + TW * TL::W + i] = INFINITY;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) ps[r * TL::PLANE + TW * TL::W + i] = 0u;
-            }
-        }
+        init_invalid(st, sm, COL, lane);
+        if (COL)    // the dummy row never changes: "no seed" in the float buffers and in every ring slot
+            for (int i = threadIdx.x; i < TL::W; i += THREADS) put_invalid(sm, TW * TL::W + i);
         const size_t plane_sz = (size_t)n * n;
         __syncthreads();
         const float* lut = sm + TL::OFF_LUT;
@@ -321,6 +358,7 @@ struct March {
         uint32_t own[TL::U], halo[TL::HV];
         // plane p (p = -1 .. steps) of the march: slab-local z = zl0 + p*k.  Planes outside the grid are staged as
         // all-"no seed" (zeros) so that the steady-state code has no special cases.
+        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
         auto fetch = [&](int p) {
             const int zl = zl0 + p * k;
             const int gz = zl + (int)a.z0;
@@ -339,20 +377,25 @@ struct March {
 #pragma unroll 1
         for (int p = -1; p <= steps; ++p) {
             const int ph = (p + 1) & 3;
-            stage(own, halo, st, sm, ph, COL, lane);
+            // column mode (sparse passes, short lattices): a plane outside the grid is not staged at all; its cache
+            // slot is marked empty and the scans skip it.  Tile mode stages it as zeros to keep one code path.
+            const bool skip = COL && !plane_in_grid(p);
+            if (!skip) stage(own, halo, st, sm, a.glut, ph, COL, lane);
             __syncthreads();
             if (p < steps) fetch(p + 1);
             if (row_ok) {
                 if (p < 1) {
-                    if (p == -1) consume<0>(c, smt, tbr, nqx, nqy, nz); else consume<1>(c, smt, tbr, nqx, nqy, nz);
+                    if (skip) { if (p == -1) c.any[0] = 0; else c.any[1] = 0; }
+                    else if (p == -1) consume<0>(c, smt, tbr, nqx, nqy, nz);
+                    else consume<1>(c, smt, tbr, nqx, nqy, nz);
                 } else {
                     const int zl = zl0 + (p - 1) * k;
                     const float nqz = -lut[2 * MAXN + zl + (int)a.z0];
                     switch (ph) {
-                        case 0: emit<0>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
-                        case 1: emit<1>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
-                        case 2: emit<2>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
-                        default: emit<3>(c, smt, tbr, nqx, nqy, nz, nqz, a, zl, gy, xs, lane); break;
+                        case 0: emit<0>(c, smt, tbr, nqx, nqy, nz, nqz, skip, a, zl, gy, xs, lane); break;
+                        case 1: emit<1>(c, smt, tbr, nqx, nqy, nz, nqz, skip, a, zl, gy, xs, lane); break;
+                        case 2: emit<2>(c, smt, tbr, nqx, nqy, nz, nqz, skip, a, zl, gy, xs, lane); break;
+                        default: emit<3>(c, smt, tbr, nqx, nqy, nz, nqz, skip, a, zl, gy, xs, lane); break;
                     }
                 }
             }
@@ -362,7 +405,7 @@ struct March {
 };
 
 template <int SS, bool FINAL, bool COL>
-__global__ void __launch_bounds__(THREADS, 2) jfa_pass_march(const PassArgs a) { March<SS, FINAL, COL>::run(a); }
+__global__ void __launch_bounds__(THREADS, VPB_MARCH_MINBLOCKS) jfa_pass_march(const PassArgs a) { March<SS, FINAL, COL>::run(a); }
 
 template <int SS, bool FINAL, bool COL>
 int launch_one(const PassArgs& a, dim3 grid, cudaStream_t st) {
@@ -399,6 +442,8 @@ int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint
     a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
     a.f = f; a.z0 = z0; a.T = T; a.k = (int)k;
     a.neg_zero = -0.0f;
+    a.glut = jfa_lut_launch(f, st);
+    if (!a.glut) return VPB_ERR_CUDA;
     const ptrdiff_t kp = (ptrdiff_t)k * n * n;
     a.contiguous = (above == mid + kp) && (below == mid - kp);
     const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
