@@ -1,0 +1,203 @@
+// cli — the reference's command line (apps/cli/main.cpp:21-235) on top of the B200 back-end.
+//
+//   cli mesh.obj [mesh2.obj ...] -n N -t 4 [-p 1|2|3] [-s] [-e] [-o out.obj] [-m iterations]
+//
+// Same options, same pipeline order (shared bounding box -> per-mesh voxelization -> CSG fold into grids[0] ->
+// JFA), same "[label]: X ms" lines and the same export file names as the reference.  `-t 4` (the default here)
+// selects Types::B200; the reference's own back-ends (-t 0..3) are not part of this build.
+// `--fused` runs the whole loop through one vpb_pipeline_host call (grids stay in HBM between stages).
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include <vplib_b200/vplib_b200.h>
+#include <vplib_b200/mesh_io.h>
+#include <vplib_b200/grid_to_mesh.h>
+
+using gridType = uint32_t;
+
+namespace {
+struct Options {
+    std::vector<std::string> filenames;
+    unsigned numVoxels = 32;
+    int type = 4;
+    std::string output = "out.obj";
+    int operation = 0;
+    bool exportPhases = false, sdf = false, fused = false, help = false;
+    unsigned blockSize = 32, iterations = 1;
+};
+
+void usage() {
+    std::printf("CLI apps to test csg voxelization (B200 back-end)\nUsage:\n  cli [OPTION...] filenames...\n\n"
+                "  -i, --filenames arg   Input filenames list\n"
+                "  -n, --num-voxels arg  Number of voxel per side (default: 32)\n"
+                "  -t, --type arg        Type of processing (4 = b200; 0..3 are the reference's own back-ends) (default: 4)\n"
+                "  -o, --output arg      Output filename (default: out.obj)\n"
+                "  -p, --operation arg   CSG Operations (1 = union, 2 = inter, 3 = diff) (default: 0)\n"
+                "  -e, --export          Exports the phases\n"
+                "  -s, --sdf             Active SDF calculation on output file\n"
+                "  -b, --block-size arg  Accepted for compatibility, unused (default: 32)\n"
+                "  -m, --benckmark arg   Number of iteration in benckmark mode (default: 1)\n"
+                "      --fused           One device-resident pipeline call instead of one call per stage\n"
+                "  -h, --help            Print usage\n");
+}
+
+bool parse(int argc, char** argv, Options& o) {
+    auto value = [&](int& i, const std::string& a, std::string& out) {
+        const size_t eq = a.find('=');
+        if (eq != std::string::npos) { out = a.substr(eq + 1); return true; }
+        if (a.size() > 2 && a[0] == '-' && a[1] != '-') { out = a.substr(2); return true; }   // -n128
+        if (i + 1 >= argc) return false;
+        out = argv[++i];
+        return true;
+    };
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        std::string v;
+        auto is = [&](const char* s, const char* l) {
+            return a == s || a == l || a.rfind(std::string(l) + "=", 0) == 0 || (a.size() > 2 && a.rfind(s, 0) == 0 && a[1] != '-');
+        };
+        if (a == "-h" || a == "--help") o.help = true;
+        else if (a == "-e" || a == "--export") o.exportPhases = true;
+        else if (a == "-s" || a == "--sdf") o.sdf = true;
+        else if (a == "--fused") o.fused = true;
+        else if (is("-n", "--num-voxels")) { if (!value(i, a, v)) return false; o.numVoxels = (unsigned)std::stoul(v); }
+        else if (is("-t", "--type")) { if (!value(i, a, v)) return false; o.type = std::stoi(v); }
+        else if (is("-o", "--output")) { if (!value(i, a, v)) return false; o.output = v; }
+        else if (is("-p", "--operation")) { if (!value(i, a, v)) return false; o.operation = std::stoi(v); }
+        else if (is("-b", "--block-size")) { if (!value(i, a, v)) return false; o.blockSize = (unsigned)std::stoul(v); }
+        else if (is("-m", "--benckmark")) { if (!value(i, a, v)) return false; o.iterations = (unsigned)std::stoul(v); }
+        else if (is("-i", "--filenames")) { if (!value(i, a, v)) return false; o.filenames.push_back(v); }
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
+        else o.filenames.push_back(a);
+    }
+    return true;
+}
+
+template <typename Func>
+void Fold(HostVoxelsGrid<gridType>& a, HostVoxelsGrid<gridType>& b, Func f) { CSG::Compute<Types::B200>(a, b, f); }
+}  // namespace
+
+int main(int argc, char** argv) {
+    cpuAssert((argc >= 2), "Need [input file]\n");
+    Options opt;
+    if (!parse(argc, argv, opt)) { usage(); return 1; }
+    if (opt.help) { usage(); return 0; }
+    cpuAssert(opt.filenames.size() >= 1, "Need [input filename]");
+    cpuAssert(opt.blockSize % 16 == 0, "Thread per voxel must be a multiple of 16");
+    cpuAssert(opt.type == static_cast<int>(Types::B200),
+              "this build only contains the B200 back-end: use -t 4 (the reference's -t 0..3 live in the reference build)");
+
+    const Types TYPE = Types::B200;
+    const CSG::Op OPERATION = static_cast<CSG::Op>(opt.operation);
+    const unsigned NUM_VOXELS = opt.numVoxels;
+    const bool BENCKMARK = opt.iterations > 1;
+    const bool EXPORT = !BENCKMARK ? opt.exportPhases : false;
+
+    std::vector<Mesh> meshes(opt.filenames.size());
+    std::vector<HostVoxelsGrid<gridType>> grids(opt.filenames.size());
+
+    // shared frame of all meshes (main.cpp:65-87)
+    float originX, originY, originZ, voxelSize;
+    {
+        std::vector<Position> coords;
+        for (size_t i = 0; i < meshes.size(); i++)
+            cpuAssert(ImportMesh(opt.filenames[i], meshes[i]), "Error in " + opt.filenames[i] + " import");
+        for (const auto& mesh : meshes) coords.insert(coords.end(), mesh.Coords.begin(), mesh.Coords.end());
+        std::pair<float, float> bbX, bbY, bbZ;
+        const float sideLength = CalculateBoundingBox(coords.data(), coords.size(), bbX, bbY, bbZ);
+        originX = bbX.first; originY = bbY.first; originZ = bbZ.first;
+        voxelSize = sideLength / NUM_VOXELS;
+    }
+
+    HostVoxelsGrid<gridType> bmGrid(NUM_VOXELS, voxelSize);
+
+    for (unsigned j = 0; j < opt.iterations; ++j) {
+        HostGrid<float> sdf;
+        if (opt.fused) {
+            // one call: every grid stays on the device between stages (include/vpb200.h: vpb_pipeline_host)
+            VPB_PROFILING_SCOPE("B200Pipeline");
+            vplib_b200::ensure_init();
+            std::vector<const float*> v; std::vector<uint64_t> nv; std::vector<const uint32_t*> t; std::vector<uint64_t> nt;
+            for (const auto& m : meshes) {
+                v.push_back(reinterpret_cast<const float*>(m.Coords.data())); nv.push_back(m.Coords.size());
+                t.push_back(m.FacesCoords.data()); nt.push_back(m.FacesCoords.size() / 3);
+            }
+            grids[0] = HostVoxelsGrid<gridType>(NUM_VOXELS, voxelSize);
+            grids[0].View().SetOrigin(originX, originY, originZ);
+            if (opt.sdf) sdf = HostGrid<float>(NUM_VOXELS, -INFINITY);
+            vplib_b200::check(vpb_pipeline_host((int)meshes.size(), v.data(), nv.data(), t.data(), nt.data(), NUM_VOXELS, voxelSize,
+                                                grids[0].Origin(), opt.operation, grids[0].Words32(), opt.sdf ? sdf.Data() : nullptr),
+                              "vpb_pipeline_host", __FILE__, __LINE__);
+            float tm[3];
+            if (vpb_last_timing(tm) == VPB_OK) {
+                vplib_b200::print_stage("B200Pipeline::Memory", tm[0] + tm[2]);
+                vplib_b200::print_stage("B200Pipeline::Processing", tm[1]);
+            }
+        } else {
+            for (size_t i = 0; i < meshes.size(); i++) {
+                auto& mesh = meshes[i];
+                auto& grid = grids[i];
+                grid = HostVoxelsGrid<gridType>(NUM_VOXELS, voxelSize);
+                grid.View().SetOrigin(originX, originY, originZ);
+                VOX::Compute<Types::B200>(grid, mesh);
+
+                if (EXPORT) {
+                    Mesh outMesh;
+                    VoxelsGridToMeshCompressed(grid.View(), outMesh);
+                    cpuAssert(ExportMesh("out/" + GetTypesString(TYPE) + "_" + GetFilename(opt.filenames[i]), outMesh),
+                              "Error in " + GetTypesString(TYPE) + " " + opt.filenames[i] + " export");
+                }
+                if (i > 0 || BENCKMARK) {
+                    auto& opGrid = !BENCKMARK ? grid : bmGrid;
+                    switch (OPERATION) {
+                        case CSG::Op::UNION: Fold(grids[0], opGrid, CSG::Union<gridType>()); break;
+                        case CSG::Op::DIFFERENCE: Fold(grids[0], opGrid, CSG::Difference<gridType>()); break;
+                        case CSG::Op::INTERSECTION: Fold(grids[0], opGrid, CSG::Intersection<gridType>()); break;
+                        case CSG::Op::VOID: break;
+                    }
+                }
+                if (BENCKMARK) break;
+            }
+        }
+
+        if (EXPORT && OPERATION != CSG::Op::VOID) {
+            Mesh outMesh;
+            VoxelsGridToMeshCompressed(grids[0].View(), outMesh);
+            cpuAssert(ExportMesh("out/csg_vox_" + GetTypesString(TYPE) + "_" + opt.output, outMesh),
+                      "Error in " + opt.output + " export (csg)");
+        }
+
+        if (opt.sdf) {
+            if (!opt.fused) {
+                sdf = HostGrid<float>(grids[0].View().VoxelsPerSide(), -INFINITY);
+                JFA::Compute<Types::B200>(grids[0], sdf);
+            }
+            if (EXPORT) {
+                Mesh outMesh;
+                VoxelsGridToMesh(grids[0].View(), sdf.View(), outMesh);
+                cpuAssert(ExportMesh("out/sdf_" + GetTypesString(TYPE) + "_" + opt.output, outMesh),
+                          "Error in " + opt.output + " export (sdf)");
+                VoxelsGridToPointCloud(grids[0].View(), sdf.View(), outMesh);
+                cpuAssert(ExportMesh("out/sdf_point_cloud_" + GetTypesString(TYPE) + "_" + opt.output, outMesh),
+                          "Error in " + opt.output + " export (sdf)");
+            }
+        }
+        if (const char* dump = std::getenv("VPB_CLI_DUMP")) {
+            // test hook: raw little-endian dump of grids[0] (and the sdf) for the parity tests
+            if (std::FILE* f = std::fopen((std::string(dump) + ".bits").c_str(), "wb")) {
+                std::fwrite(grids[0].Words32(), 4, ((size_t)NUM_VOXELS * NUM_VOXELS * NUM_VOXELS + 31) / 32, f);
+                std::fclose(f);
+            }
+            if (opt.sdf)
+                if (std::FILE* f = std::fopen((std::string(dump) + ".sdf").c_str(), "wb")) {
+                    std::fwrite(sdf.Data(), 4, sdf.Size(), f);
+                    std::fclose(f);
+                }
+        }
+    }
+    vpb_shutdown();
+    return 0;
+}
