@@ -22,6 +22,9 @@
 
 namespace vpb {
 
+int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                          uint32_t* seeds, cudaStream_t st);
 int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
                           uint32_t* seeds, cudaStream_t st);
@@ -243,11 +246,13 @@ int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* 
     VPB_REQUIRE(f.n > 0 && f.n <= MAX_N && z0 < z1 && z1 <= f.n, "jfa_pass: unsupported n=%u slab [%u,%u)", f.n, z0, z1);
     VPB_REQUIRE(k >= 1 && k < f.n, "jfa_pass: bad step %u", k);
     VPB_REQUIRE(!sdf || words_full, "jfa_pass: final pass needs the occupancy grid for the sign");
-    // VPB_JFA_KERNEL=gather forces the straightforward kernel (tests compare the two implementations)
+    // VPB_JFA_KERNEL=gather|march forces the straightforward / the register-cache kernel (tests compare all three)
     const char* env = getenv("VPB_JFA_KERNEL");
-    const bool force_gather = env && strcmp(env, "gather") == 0;
-    if (force_gather) return jfa_pass_gather_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
-    return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    if (env && strcmp(env, "gather") == 0)
+        return jfa_pass_gather_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    if (env && strcmp(env, "march") == 0)
+        return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    return jfa_pass_flood_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
 }
 
 int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,

@@ -1,0 +1,483 @@
+// JFA flood pass, "scatter + integer keys" version for sm_100a (N % 64 == 0, N <= 1024, k a power of two).
+//
+// Same result as jfa_pass_gather / the reference (vplib/src/jfa/sequential.cpp:68-125, jfa/jfa.h:19-20), bit for bit.
+// What is different from jfa_tiled.cu (the z-march with a register cache, kept as the fallback):
+//
+//  * SCATTER instead of gather.  A staged input plane P is candidate dz = -1 of output plane P+k, dz = 0 of P and
+//    dz = +1 of P-k.  One sweep over the 9 (dy,dx) candidates of P feeds the running winners of those three output
+//    planes, so (dx*dx + dy*dy) is computed once per (candidate, voxel) without a 72-register cache, and the kernel
+//    runs at ~64 registers / 32 warps per SM instead of 121 / 16.
+//  * INTEGER KEYS instead of FSETP + SEL + FMNMX.  The reference keeps the first candidate in scan order (dz outer,
+//    dy, dx inner, the voxel's own seed before all) among those with the smallest float distance.  A positive float
+//    orders like its bit pattern, and every distance that can occur lies in [vs^2/4, 2^29 vs^2): after subtracting
+//    a base exponent the bits fit in 28, which leaves 4 bits for the (dy,dx) code.  key = bits(d) * 16 + code is one
+//    LEA/IMAD, and the 9 candidates of a plane reduce with 4 three-input VIMNMX3 per voxel.  The three planes (and
+//    the own seed) are merged with `(new | 15) < old`, i.e. strictly-smaller-distance-wins, in scan order.
+//    profiles/r01_ubench.txt: 7.6 cycles per candidate x 2 voxels x warp against 11.0 for the FSETP/SEL form.
+//  * The key trick needs a sane frame (positions strictly increasing by >= 0.75 voxelSize, exponents in range); the
+//    launcher checks that on the host with the reference's own expression and otherwise uses jfa_tiled.cu.
+//
+// All float work is packed FADD2/FFMA2 on two x-adjacent voxels (individually rounded lanes, see sq2()).
+#include "common.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace vpb {
+
+const float* jfa_lut_launch(const Frame& f, cudaStream_t st);   // jfa.cu
+int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                          uint32_t* seeds, cudaStream_t st);       // jfa_tiled.cu
+
+namespace {
+
+#ifndef VPB_FLOOD_MINBLOCKS
+#define VPB_FLOOD_MINBLOCKS 3
+#endif
+#ifndef VPB_FLOOD_LZ
+#define VPB_FLOOD_LZ 32
+#endif
+
+constexpr int TW = 8;            // warps per CTA == output rows per CTA
+constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
+constexpr int THREADS = TW * 32;
+constexpr int MAXN = 1024;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t OWN_CODE = 5;   // (dy,dx) code of the centre: row 1, column 1
+
+struct FloodArgs {
+    const uint32_t* src[3];   // below / mid / above (see vpb_jfa_pass_dev)
+    uint32_t* dst;
+    const uint32_t* words;    // occupancy (FINAL only)
+    float* sdf;               // FINAL only
+    uint32_t* seeds;          // FINAL only, optional
+    const float* glut;        // px | py | pz, 3 * MAXN floats
+    uint32_t n, z0, T;
+    int k;
+    int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
+    int lz, segs_z;           // outputs per march segment, segments per z-lattice column
+    int tiles_y;              // tile mode: 8-row tiles per y-lattice column
+    int column_mode;          // y lattice has <= 8 points: a CTA takes whole columns of 8/lp y-residues
+    int lp, ly;               // column mode: padded (power of two) and true lattice length in y
+    int rows;                 // staged rows per plane (tile: 10; column: 8 + 8/lp + 1)
+    uint32_t key_base;        // bits subtracted from every distance: (E0 << 23)
+    uint32_t key_k0;          // -(key_base * 16) mod 2^32
+    float bigz;               // z coordinate staged for "no seed": distance lands above every real one, below the key range
+    float neg_zero;           // -0.0f, deliberately a RUNTIME value: see sq2()
+};
+
+template <int SS>
+struct Tile {
+    static constexpr int W = SEG + 2 * SS;           // staged window per row (SS = 64: three 64-wide segments)
+    static constexpr int U = (W + 31) / 32;          // own-row entries per lane
+    static constexpr int HV = (2 * W + THREADS - 1) / THREADS;   // halo-row entries per thread (tile mode)
+    static constexpr bool ALIGNED = (SS % 2) == 0;
+};
+
+__device__ __forceinline__ float2 ld2(const float* p, bool aligned) {
+    if (aligned) return *reinterpret_cast<const float2*>(p);
+    return make_float2(p[0], p[1]);
+}
+
+// x*x for two lanes, individually rounded; see jfa_tiled.cu for why this is an FFMA2 with a run-time -0.0f
+__device__ __forceinline__ float2 sq2(float2 x, float2 nz) { return __ffma2_rn(x, x, nz); }
+
+__device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
+
+template <int SS, bool FINAL>
+struct Flood {
+    using TL = Tile<SS>;
+
+    static __device__ __forceinline__ int gx_of(int i, int xs, int k) {
+        return (SS < 64) ? (xs - SS + i) : (xs + (i / SEG - 1) * k + (i % SEG));
+    }
+
+    // running winner of one output plane, for the thread's two voxels
+    struct Acc {
+        uint32_t key[2];
+        uint32_t tag[2];   // ring-slot word offset of the plane the winner came from
+    };
+
+    static __device__ __forceinline__ void merge(uint32_t& key, uint32_t& tag, uint32_t cand, uint32_t cand_tag) {
+        const bool win = (cand | 15u) < key;          // strictly smaller distance: later candidates lose ties
+        key = win ? cand : key;
+        tag = win ? cand_tag : tag;
+    }
+
+    static __device__ __forceinline__ void run(const FloodArgs& a) {
+        extern __shared__ float sm[];
+        const int n = (int)a.n, k = a.k;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int plane_words = a.rows * TL::W;                   // entries per staged plane
+        float* const lut = sm;                                     // px | py | pz
+        float* const fbuf = sm + 3 * MAXN;                         // 2 x (fx | fy | fz) planes
+        uint32_t* const ring = reinterpret_cast<uint32_t*>(fbuf + 6 * plane_words);   // 4 packed planes
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(a.glut);
+            float4* s4 = reinterpret_cast<float4*>(lut);
+            for (int i = threadIdx.x; i < 3 * MAXN / 4; i += THREADS) s4[i] = __ldg(g4 + i);
+        }
+        // ---- tile coordinates ---------------------------------------------------------------------------------
+        const int xs = blockIdx.x * SEG;
+        const int rz = blockIdx.z / a.segs_z, sz = blockIdx.z - rz * a.segs_z;
+        const int zl0 = rz + sz * a.lz * k;                       // slab-local z of the first output plane
+        int steps = 0;
+        for (int j = 0; j < a.lz; ++j) if (zl0 + j * k < (int)a.T) ++steps;
+        if (steps == 0) return;
+        int gy, myrow;
+        bool row_ok;
+        if (!a.column_mode) {
+            const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
+            gy = ry + (ty * TW + warp) * k;
+            row_ok = gy < n;
+            myrow = warp + 1;
+        } else {
+            const int g = warp / a.lp, j = warp - g * a.lp;
+            const int ry = blockIdx.y * (TW / a.lp) + g;
+            gy = ry + j * k;
+            row_ok = ry < k && j < a.ly && gy < n;
+            myrow = g * (a.lp + 1) + 1 + j;                        // every residue group sits between two dummy rows
+        }
+        // ---- what this thread stages (plane-invariant) ----------------------------------------------------------
+        int own_off[TL::U], halo_off[TL::HV], halo_sm[TL::HV];
+        const int own_sm = myrow * TL::W + lane;
+#pragma unroll
+        for (int u = 0; u < TL::U; ++u) {
+            const int i = lane + 32 * u;
+            const int gx = gx_of(i, xs, k);
+            own_off[u] = (row_ok && i < TL::W && gx >= 0 && gx < n) ? gy * n + gx : -1;
+        }
+#pragma unroll
+        for (int v = 0; v < TL::HV; ++v) {
+            halo_off[v] = -1;
+            halo_sm[v] = -1;
+            const int h = (int)threadIdx.x + THREADS * v;
+            if (!a.column_mode && h < 2 * TL::W) {
+                const int top = h >= TL::W;                        // 0: staged row 0, 1: staged row 9
+                const int i = h - top * TL::W;
+                const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
+                const int hy = ry + (ty * TW + (top ? TW : -1)) * k;
+                const int gx = gx_of(i, xs, k);
+                halo_sm[v] = (top ? (TW + 1) : 0) * TL::W + i;
+                if (hy >= 0 && hy < n && gx >= 0 && gx < n) halo_off[v] = hy * n + gx;
+            }
+        }
+        __syncthreads();                                           // LUT visible
+        const float inv_x = lut[0], inv_y = lut[MAXN];             // coordinates staged for "no seed"
+        if (a.column_mode) {
+            // dummy rows never change: "no seed" in both float buffers and in every ring slot
+            const int groups = TW / a.lp;
+            for (int d = 0; d <= groups; ++d)
+                for (int i = threadIdx.x; i < TL::W; i += THREADS) {
+                    const int e = d * (a.lp + 1) * TL::W + i;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        float* f = fbuf + b * 3 * plane_words;
+                        f[e] = inv_x; f[plane_words + e] = inv_y; f[2 * plane_words + e] = a.bigz;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) ring[r * plane_words + e] = 0u;
+                }
+        }
+        const size_t plane_sz = (size_t)n * n;
+        const int x0 = xs + 2 * lane;
+        const float2 nqx = make_float2(-lut[x0], -lut[x0 + 1]);
+        const float qy_s = row_ok ? lut[MAXN + gy] : 0.0f;
+        const float2 nqy = make_float2(-qy_s, -qy_s);
+        const float2 nz = make_float2(a.neg_zero, a.neg_zero);
+        const int tbase = (myrow - 1) * TL::W + 2 * lane;          // candidate (r, c) of this thread: tbase + r*W + c*SS
+
+        uint32_t own[TL::U], halo[TL::HV];
+        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
+        auto fetch = [&](int p) {
+            const int zl = zl0 + p * k;
+            const uint32_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
+                                              : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
+#pragma unroll
+            for (int u = 0; u < TL::U; ++u) own[u] = own_off[u] >= 0 ? __ldg(pp + own_off[u]) : 0u;
+            if (!a.column_mode) {
+#pragma unroll
+                for (int v = 0; v < TL::HV; ++v) halo[v] = halo_off[v] >= 0 ? __ldg(pp + halo_off[v]) : 0u;
+            }
+        };
+        auto put = [&](float* f, uint32_t* ps, int e, uint32_t s) {
+            const char* l = reinterpret_cast<const char*>(lut);
+            f[e] = *reinterpret_cast<const float*>(l + (s & 0xFFCu));
+            f[plane_words + e] = *reinterpret_cast<const float*>(l + 4 * MAXN + ((s >> 10) & 0xFFCu));
+            const float z = *reinterpret_cast<const float*>(l + 8 * MAXN + ((s >> 20) & 0xFFCu));
+            f[2 * plane_words + e] = s ? z : a.bigz;
+            ps[e] = s;
+        };
+        auto stage = [&](int p) {
+            float* f = fbuf + (p & 1) * 3 * plane_words;
+            uint32_t* ps = ring + ((p + 1) & 3) * plane_words;
+#pragma unroll
+            for (int u = 0; u < TL::U; ++u)
+                if (TL::W % 32 == 0 || lane + 32 * u < TL::W) put(f, ps, own_sm + 32 * u, own[u]);
+            if (!a.column_mode) {
+#pragma unroll
+                for (int v = 0; v < TL::HV; ++v)
+                    if (halo_sm[v] >= 0) put(f, ps, halo_sm[v], halo[v]);
+            }
+        };
+
+        Acc acc[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { acc[s].key[0] = acc[s].key[1] = NONE; acc[s].tag[0] = acc[s].tag[1] = 0u; }
+
+        // one input plane p: candidates dz=-1 of output p+1 (slot SN), dz=0 of output p (slot SC), dz=+1 of output
+        // p-1 (slot SP), then output p-1 is complete and written.
+        auto step = [&](int p, Acc& accN, Acc& accC, Acc& accP) {
+            const bool in_grid = plane_in_grid(p);
+            if (row_ok && in_grid) {
+                const float* fb = fbuf + (p & 1) * 3 * plane_words + tbase;
+                const uint32_t tag = (uint32_t)(((p + 1) & 3) * plane_words);
+                const int zN = min(max(zl0 + (p + 1) * k + (int)a.z0, 0), MAXN - 1);
+                const int zC = min(max(zl0 + p * k + (int)a.z0, 0), MAXN - 1);
+                const int zP = min(max(zl0 + (p - 1) * k + (int)a.z0, 0), MAXN - 1);
+                const float qn = -lut[2 * MAXN + zN], qc = -lut[2 * MAXN + zC], qp = -lut[2 * MAXN + zP];
+                const float2 nq[3] = {make_float2(qn, qn), make_float2(qc, qc), make_float2(qp, qp)};
+                uint32_t g[3][2], carry[3][2], ownk[2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    uint32_t kk[3][3][2];   // [target][column][voxel]
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int off = r * TL::W + c * SS;
+                        const float2 fx = ld2(fb + off, TL::ALIGNED);
+                        const float2 fy = ld2(fb + plane_words + off, TL::ALIGNED);
+                        const float2 fz = ld2(fb + 2 * plane_words + off, TL::ALIGNED);
+                        const float2 ddx = __fadd2_rn(fx, nqx);    // seed - voxel (the exact negation is folded into nq*)
+                        const float2 ddy = __fadd2_rn(fy, nqy);
+                        const float2 xy = __fadd2_rn(sq2(ddx, nz), sq2(ddy, nz));
+                        const uint32_t kc = a.key_k0 + (uint32_t)(r * 4 + c);
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const float2 ddz = __fadd2_rn(fz, nq[t]);
+                            const float2 d = __fadd2_rn(xy, sq2(ddz, nz));   // ((dx*dx)+(dy*dy)) + (dz*dz)
+                            kk[t][c][0] = __float_as_uint(d.x) * 16u + kc;
+                            kk[t][c][1] = __float_as_uint(d.y) * 16u + kc;
+                            if (t == 1 && r == 1 && c == 1) {
+                                // the voxel's own seed: scanned first by the reference.  Distance 0 (the voxel IS a
+                                // seed) would wrap below the key base: give it the smallest key there is.
+                                ownk[0] = d.x == 0.0f ? OWN_CODE : kk[t][c][0];
+                                ownk[1] = d.y == 0.0f ? OWN_CODE : kk[t][c][1];
+                            }
+                        }
+                    }
+                    // 9 (8 for the own plane) candidates per target reduce with four 3-input minima
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            if (r == 0) {
+                                g[t][v] = min3(kk[t][0][v], kk[t][1][v], kk[t][2][v]);
+                            } else if (r == 1) {
+                                if (t == 1) {
+                                    g[t][v] = min3(g[t][v], kk[t][0][v], kk[t][2][v]);
+                                } else {
+                                    g[t][v] = min3(g[t][v], kk[t][0][v], kk[t][1][v]);
+                                    carry[t][v] = kk[t][2][v];
+                                }
+                            } else {
+                                if (t == 1) {
+                                    g[t][v] = min3(g[t][v], kk[t][0][v], kk[t][1][v]);
+                                    g[t][v] = min(g[t][v], kk[t][2][v]);
+                                } else {
+                                    g[t][v] = min3(g[t][v], carry[t][v], kk[t][0][v]);
+                                    g[t][v] = min3(g[t][v], kk[t][1][v], kk[t][2][v]);
+                                }
+                            }
+                        }
+                }
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    // output p+1: this plane is its first group
+                    accN.key[v] = g[0][v];
+                    accN.tag[v] = tag;
+                    // output p: own seed first (keeps ties against the dz=-1 group), then this plane's 8 neighbours
+                    {
+                        const bool prev_wins = (accC.key[v] | 15u) < ownk[v];
+                        accC.key[v] = prev_wins ? accC.key[v] : ownk[v];
+                        accC.tag[v] = prev_wins ? accC.tag[v] : tag;
+                    }
+                    merge(accC.key[v], accC.tag[v], g[1][v], tag);
+                    // output p-1: last group
+                    merge(accP.key[v], accP.tag[v], g[2][v], tag);
+                }
+            } else if (row_ok) {
+                accN.key[0] = accN.key[1] = NONE;                  // plane outside the grid: no dz=-1 group for output p+1
+            }
+            // ---- output plane p-1 is complete ---------------------------------------------------------------------
+            if (row_ok && p >= 1) {
+                const int zl = zl0 + (p - 1) * k;
+                uint32_t s2[2];
+                float d2[2];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const uint32_t key = accP.key[v];
+                    const uint32_t code = key & 15u;
+                    const uint32_t e = accP.tag[v] + (uint32_t)tbase + (code >> 2) * TL::W + (code & 3u) * SS + v;
+                    s2[v] = ring[e];
+                    if (FINAL) {
+                        const float d = (key >> 4) ? __uint_as_float((key >> 4) + a.key_base) : 0.0f;
+                        d2[v] = s2[v] ? d : INFINITY;
+                    }
+                }
+                const size_t vox = ((size_t)zl * n + gy) * n + x0;
+                if (!FINAL) {
+                    *reinterpret_cast<uint2*>(a.dst + vox) = make_uint2(s2[0], s2[1]);
+                } else {
+                    const size_t bit = ((size_t)(zl + a.z0) * n + gy) * n + x0;
+                    const uint32_t w = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
+                    *reinterpret_cast<float2*>(a.sdf + vox) = make_float2((w & 1u) ? d2[0] : -d2[0], (w & 2u) ? d2[1] : -d2[1]);
+                    if (a.seeds) *reinterpret_cast<uint2*>(a.seeds + vox) = make_uint2(jfa_public(s2[0]), jfa_public(s2[1]));
+                }
+            }
+        };
+
+        // ---- march: planes p = -1 .. steps ------------------------------------------------------------------------
+        if (plane_in_grid(-1)) { fetch(-1); stage(-1); }
+        int p = -1;
+        auto iteration = [&](Acc& accN, Acc& accC, Acc& accP) {
+            __syncthreads();                                       // plane p staged by everyone, plane p-1 consumed
+            const bool more = p < steps && plane_in_grid(p + 1);
+            if (more) fetch(p + 1);
+            step(p, accN, accC, accP);
+            if (more) stage(p + 1);
+            ++p;
+        };
+#pragma unroll 1
+        while (true) {
+            // slot of output o is (o + 1) % 3; p = -1 + 3m here
+            iteration(acc[1], acc[0], acc[2]);
+            if (p > steps) break;
+            iteration(acc[2], acc[1], acc[0]);
+            if (p > steps) break;
+            iteration(acc[0], acc[2], acc[1]);
+            if (p > steps) break;
+        }
+    }
+};
+
+template <int SS, bool FINAL>
+__global__ void __launch_bounds__(THREADS, VPB_FLOOD_MINBLOCKS) jfa_pass_flood(const FloodArgs a) { Flood<SS, FINAL>::run(a); }
+
+size_t smem_bytes(int rows, int W) { return ((size_t)3 * MAXN + (size_t)10 * rows * W) * 4; }
+
+template <int SS, bool FINAL>
+int launch_one(const FloodArgs& a, dim3 grid, cudaStream_t st) {
+    static size_t configured = 0;
+    const size_t bytes = smem_bytes(a.rows, Tile<SS>::W);
+    if (bytes > configured) {
+        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_flood<SS, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
+    }
+    jfa_pass_flood<SS, FINAL><<<grid, THREADS, bytes, st>>>(a);
+    VPB_LAUNCH_CHECK();
+    return VPB_OK;
+}
+
+template <int SS>
+int launch_ss(const FloodArgs& a, dim3 grid, bool fin, cudaStream_t st) {
+    return fin ? launch_one<SS, true>(a, grid, st) : launch_one<SS, false>(a, grid, st);
+}
+
+// The key trick is exact iff (checked here with the reference's own float expression, evaluated on the host without
+// contraction): positions increase by at least 0.75 voxelSize per index on every axis (so every non-zero coordinate
+// difference is >= 0.75 vs and every non-zero distance >= vs^2 / 2), the grid is at most 1.01 N vs wide, and the
+// exponents involved are ordinary.  Then bits(d) - key_base is in [0, 2^28) for real distances and for the "no seed"
+// sentinel.
+bool frame_supports_keys(const Frame& f, uint32_t* key_base, float* bigz) {
+    const float vs = f.vs;
+    if (!(vs > 0.0f) || !std::isfinite(vs)) return false;
+    volatile float vs2v = vs * vs;
+    const float vs2 = vs2v;
+    if (!(vs2 > 1e-30f) || !(vs2 < 1e20f)) return false;
+    int e;
+    std::frexp(vs2, &e);                       // vs2 = m * 2^e, m in [0.5, 1)  ->  2^(e-1) <= vs2
+    const int E0 = (e - 1) - 2 + 127;           // 2^(E0-127) <= vs2 / 4
+    if (E0 < 1 || E0 + 32 > 254) return false;
+    const float o[3] = {f.ox, f.oy, f.oz};
+    float zmax = 0.0f;
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!std::isfinite(o[ax])) return false;
+        volatile float prev = 0.0f, first = 0.0f;
+        for (uint32_t i = 0; i < f.n; ++i) {
+            volatile float t = (float)i * vs;
+            volatile float p = o[ax] + t;
+            if (i == 0) first = p;
+            else {
+                volatile float gap = p - prev;
+                if (!(gap >= 0.75f * vs)) return false;
+            }
+            prev = p;
+        }
+        volatile float width = prev - first;
+        if (!(width <= 1.01f * (float)f.n * vs)) return false;
+        if (ax == 2) zmax = prev;
+    }
+    volatile float far = zmax + 8192.0f * vs;   // (far - qz)^2 in [2^26, 2^26.4] vs^2: above 3 N^2 vs^2, below 2^29 vs^2
+    if (!std::isfinite(far)) return false;
+    volatile float chk = far - zmax;
+    if (!(chk >= 8000.0f * vs) || !(chk <= 8400.0f * vs)) return false;   // origin so large that the sentinel collapses
+    *key_base = (uint32_t)E0 << 23;
+    *bigz = far;
+    return true;
+}
+
+}  // namespace
+
+int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                          uint32_t* seeds, cudaStream_t st) {
+    const uint32_t n = f.n, T = z1 - z0;
+    const bool k_ok = k >= 64 ? (k & (k - 1)) == 0 : (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32);
+    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
+    FloodArgs a;
+    if (n % SEG != 0 || n > MAXN || !k_ok || !align_ok || !frame_supports_keys(f, &a.key_base, &a.bigz))
+        return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    a.key_k0 = 0u - a.key_base * 16u;
+    a.src[0] = below; a.src[1] = mid; a.src[2] = above;
+    a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
+    a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
+    a.neg_zero = -0.0f;
+    a.glut = jfa_lut_launch(f, st);
+    if (!a.glut) return VPB_ERR_CUDA;
+    const ptrdiff_t kp = (ptrdiff_t)k * n * n;
+    a.contiguous = (above == mid + kp) && (below == mid - kp);
+    const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
+    a.lz = a.contiguous ? (cz < VPB_FLOOD_LZ ? cz : VPB_FLOOD_LZ) : 1;
+    a.segs_z = (cz + a.lz - 1) / a.lz;
+    const int cy = (int)((n + k - 1) / k);                      // lattice points per y column
+    const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
+    unsigned grid_y;
+    a.column_mode = cy <= TW;
+    a.tiles_y = 1; a.lp = TW; a.ly = cy;
+    if (a.column_mode) {
+        a.lp = 1;
+        while (a.lp < cy) a.lp <<= 1;
+        const int res_per_cta = TW / a.lp;
+        grid_y = (res_y + res_per_cta - 1) / res_per_cta;
+        a.rows = TW + res_per_cta + 1;
+    } else {
+        a.tiles_y = (cy + TW - 1) / TW;
+        grid_y = res_y * a.tiles_y;
+        a.rows = TW + 2;
+    }
+    dim3 grid(n / SEG, grid_y, res_z * a.segs_z);
+    VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
+    const bool fin = sdf != nullptr;
+    switch (k >= 64 ? 64 : (int)k) {
+        case 64: return launch_ss<64>(a, grid, fin, st);
+        case 32: return launch_ss<32>(a, grid, fin, st);
+        case 16: return launch_ss<16>(a, grid, fin, st);
+        case 8: return launch_ss<8>(a, grid, fin, st);
+        case 4: return launch_ss<4>(a, grid, fin, st);
+        case 2: return launch_ss<2>(a, grid, fin, st);
+        default: return launch_ss<1>(a, grid, fin, st);
+    }
+}
+
+}  // namespace vpb

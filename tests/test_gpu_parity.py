@@ -195,12 +195,16 @@ def test_tiled_pass_equals_gather_pass_and_oracle(mesh, n, meshes, oracle, vpb, 
     v, t = meshes[mesh]
     origin, vs = oracle.frame(v, n)
     words = oracle.voxelize(v, t, n, vs, origin)
-    sdf_t, seeds_t = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    sdf_t, seeds_t = vpb.jfa_host(words, n, vs, origin, want_seeds=True)      # jfa_flood.cu (default)
     monkeypatch.setenv("VPB_JFA_KERNEL", "gather")
     sdf_g, seeds_g = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_KERNEL", "march")
+    sdf_m, seeds_m = vpb.jfa_host(words, n, vs, origin, want_seeds=True)      # jfa_tiled.cu (fallback)
     monkeypatch.delenv("VPB_JFA_KERNEL")
     assert np.array_equal(sdf_t.view(np.uint32), sdf_g.view(np.uint32))
     assert np.array_equal(seeds_t, seeds_g)
+    assert np.array_equal(sdf_m.view(np.uint32), sdf_g.view(np.uint32))
+    assert np.array_equal(seeds_m, seeds_g)
     if n <= 192:
         osdf, oseeds = oracle.jfa(words, n, vs, origin, want_seeds=True)
         assert np.array_equal(sdf_t.view(np.uint32), osdf.view(np.uint32))
@@ -215,12 +219,17 @@ def test_tiled_pass_on_random_dense_ties(oracle, vpb):
         words = rng.integers(0, 2 ** 32, nw, dtype=np.uint32) & rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
         sparse = np.zeros(nw, np.uint32)
         sparse[rng.integers(0, nw, 40)] = 1 << 7          # a few isolated seeds: exercises the sparse early passes
+        # frames: a noisy one, a "nice" one (power-of-two voxel size: every integer tie is an exact float tie, so the
+        # scan-order tie-break decides everywhere), and one whose origin is so far from zero that positions collapse
+        # (the key-based flood kernel must refuse it and fall back to the register-cache kernel)
+        frames = [(0.0371, [-3.25, 0.5, 11.0]), (0.0625, [-1.0, -1.0, -1.0]), (0.001, [70000.0, -3.0, 0.25])]
         for w in (words, sparse):
-            o = np.array([-3.25, 0.5, 11.0], np.float32)
-            sdf, seeds = vpb.jfa_host(w, n, 0.0371, o, want_seeds=True)
-            osdf, oseeds = oracle.jfa(w, n, 0.0371, o, want_seeds=True)
-            assert np.array_equal(sdf.view(np.uint32), osdf.view(np.uint32))
-            assert np.array_equal(seeds, _public_seeds(oseeds, n))
+            for vs, org in frames:
+                o = np.array(org, np.float32)
+                sdf, seeds = vpb.jfa_host(w, n, vs, o, want_seeds=True)
+                osdf, oseeds = oracle.jfa(w, n, vs, o, want_seeds=True)
+                assert np.array_equal(sdf.view(np.uint32), osdf.view(np.uint32)), (n, vs, org)
+                assert np.array_equal(seeds, _public_seeds(oseeds, n)), (n, vs, org)
 
 
 # ---------------------------------------------------------------------------------------------- device-resident + slabs
