@@ -186,6 +186,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     n = args.n
     meshes, origin, vs = load_workload(n, args.faces)
@@ -213,6 +216,8 @@ def run_ours(args):
         sampler.start()
     launches0 = capi.kernel_launches()
     pipe.pass_events.clear()
+    if hasattr(pipe, "stage_events"):
+        pipe.stage_events = []
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -234,6 +239,20 @@ def run_ours(args):
     slab_voxels = pipe.slab_voxels if world > 1 else n ** 3
     pass_avg = {k: float(np.mean(v)) for k, v in pass_ms.items()}
     mean_pass_ms = float(np.mean([np.mean(v) for v in pass_ms.values()])) if pass_ms else None
+    stage_ms = None
+    if getattr(pipe, "stage_events", None):
+        stage_ms = {}
+        ev = pipe.stage_events
+        for (la, ea), (lb, eb) in zip(ev, ev[1:]):
+            if lb != "start":
+                stage_ms[lb] = stage_ms.get(lb, 0.0) + ea.elapsed_time(eb) / args.steps
+    stage_ranks = None
+    if stage_ms and world > 1:
+        keys = sorted(stage_ms)
+        t = torch.tensor([stage_ms[k_] for k_ in keys], device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        stage_ranks = {k_: [round(float(a[i]), 2) for a in allt] for i, k_ in enumerate(keys)}
     peak, peak_src = hbm_peak()
     alg_bytes = 8.0 * slab_voxels  # 4 B state read + 4 B state (or sdf) write per voxel per pass
     achieved = alg_bytes / (mean_pass_ms * 1e-3) / 1e9 if mean_pass_ms else None
@@ -287,7 +306,9 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": "union",
                    "l2": "per-step working set (2 x 4.3 GB seed state + 4.3 GB sdf) >> 126 MB L2, no flush needed",
-                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass"},
+                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass",
+                   **({"stage_ms_rank0": stage_ms} if stage_ms else {}),
+                   **({"stage_ms_by_rank": stage_ranks} if stage_ranks else {})},
         "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the log2(N) passes of a step)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,

@@ -208,6 +208,17 @@ int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t*
                            stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
+int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes, uint32_t* dst,
+                          uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float vs, const float origin[3],
+                          const uint32_t* words_full, float* sdf, uint32_t* seeds, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && slab_states && dst, "jfa_pass_peer: null argument");
+    VPB_REQUIRE(n > 0 && n <= 1024 && z0 < z1 && z1 <= n && k >= 1 && k < n, "jfa_pass_peer: bad n=%u slab [%u,%u) k=%u", n, z0, z1, k);
+    VPB_REQUIRE(!sdf || words_full, "jfa_pass_peer: final pass needs the occupancy grid for the sign");
+    return jfa_pass_flood_peer_launch(slab_states, world, slab_planes, dst, make_frame(n, vs, origin), z0, z1, k, words_full,
+                                      sdf, seeds, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
 int vpb_jfa_finalize_dev(const uint32_t* state, uint32_t n, uint32_t z0, uint32_t z1, float vs, const float origin[3],
                          const uint32_t* words_full, float* sdf, uint32_t* seeds, void* stream) {
     VPB_TRY(require_ready());

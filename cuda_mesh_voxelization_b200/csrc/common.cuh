@@ -95,6 +95,9 @@ int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_
 int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,
                     uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
                     cudaStream_t st);
+int jfa_pass_flood_peer_launch(const uint32_t* const* slabs, uint32_t world, uint32_t slab_planes, uint32_t* dst,
+                               const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                               float* sdf, uint32_t* seeds, cudaStream_t st);
 int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
                         float* sdf, uint32_t* seeds, cudaStream_t st);
 

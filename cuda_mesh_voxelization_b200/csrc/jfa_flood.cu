@@ -56,6 +56,10 @@ struct FloodArgs {
     uint32_t n, z0, T;
     int k;
     int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
+    // peer mode (multi-GPU without halo copies): plane gz of the state lives at slab[gz / slab_T] + (gz % slab_T) planes,
+    // slab[r] being rank r's slab, mapped into this process (NVLink peer memory); loads go straight over NVLink
+    const uint32_t* slab[8];
+    int peer, slab_T, slab_shift;   // slab_shift >= 0 when slab_T is a power of two
     int lz, segs_z;           // outputs per march segment, segments per z-lattice column
     int tiles_y;              // tile mode: 8-row tiles per y-lattice column
     int column_mode;          // y lattice has <= 8 points: a CTA takes whole columns of 8/lp y-residues
@@ -192,8 +196,15 @@ struct Flood {
         auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
         auto fetch = [&](int p) {
             const int zl = zl0 + p * k;
-            const uint32_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
-                                              : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
+            const uint32_t* pp;
+            if (a.peer) {
+                const int gz = zl + (int)a.z0;
+                const int r = a.slab_shift >= 0 ? (gz >> a.slab_shift) : (gz / a.slab_T);
+                pp = a.slab[r] + (size_t)(gz - r * a.slab_T) * plane_sz;
+            } else {
+                pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
+                                  : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
+            }
 #pragma unroll
             for (int u = 0; u < TL::U; ++u) own[u] = own_off[u] >= 0 ? __ldg(pp + own_off[u]) : 0u;
             if (!a.column_mode) {
@@ -429,24 +440,55 @@ bool frame_supports_keys(const Frame& f, uint32_t* key_base, float* bigz) {
 
 }  // namespace
 
+static bool flood_shape_ok(const Frame& f, uint32_t k, const void* dst, const void* sdf, const void* seeds) {
+    const bool k_ok = k >= 64 ? (k & (k - 1)) == 0 : (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32);
+    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
+    return f.n % SEG == 0 && f.n <= MAXN && k_ok && align_ok;
+}
+
+static int flood_launch_common(FloodArgs& a, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st);
+
 int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
                           uint32_t* seeds, cudaStream_t st) {
-    const uint32_t n = f.n, T = z1 - z0;
-    const bool k_ok = k >= 64 ? (k & (k - 1)) == 0 : (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32);
-    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
     FloodArgs a;
-    if (n % SEG != 0 || n > MAXN || !k_ok || !align_ok || !frame_supports_keys(f, &a.key_base, &a.bigz))
+    if (!flood_shape_ok(f, k, dst, sdf, seeds) || !frame_supports_keys(f, &a.key_base, &a.bigz))
         return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
-    a.key_k0 = 0u - a.key_base * 16u;
     a.src[0] = below; a.src[1] = mid; a.src[2] = above;
     a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
+    a.peer = 0; a.slab_T = 0; a.slab_shift = -1;
+    for (auto& p : a.slab) p = nullptr;
+    const ptrdiff_t kp = (ptrdiff_t)k * f.n * f.n;
+    a.contiguous = (above == mid + kp) && (below == mid - kp);
+    return flood_launch_common(a, f, z0, z1, k, st);
+}
+
+// Peer mode: every rank's slab of the source state is addressable from this GPU (NVLink peer mapping); no halo copies.
+// Returns VPB_ERR_ARG for shapes/frames the key-based kernel does not cover (the caller then uses the exchange path).
+int jfa_pass_flood_peer_launch(const uint32_t* const* slabs, uint32_t world, uint32_t slab_planes, uint32_t* dst,
+                               const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                               float* sdf, uint32_t* seeds, cudaStream_t st) {
+    FloodArgs a;
+    VPB_REQUIRE(slabs && world >= 1 && world <= 8 && slab_planes * world == f.n, "jfa_pass_peer: bad slab table (world=%u, planes=%u)", world, slab_planes);
+    VPB_REQUIRE(flood_shape_ok(f, k, dst, sdf, seeds) && frame_supports_keys(f, &a.key_base, &a.bigz),
+                "jfa_pass_peer: shape or frame not covered by the flood kernel (n=%u, k=%u)", f.n, k);
+    a.src[0] = a.src[1] = a.src[2] = nullptr;
+    for (uint32_t r = 0; r < 8; ++r) a.slab[r] = r < world ? slabs[r] : nullptr;
+    a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
+    a.peer = 1; a.slab_T = (int)slab_planes; a.slab_shift = -1;
+    if ((slab_planes & (slab_planes - 1)) == 0) { a.slab_shift = 0; while ((1u << a.slab_shift) < slab_planes) ++a.slab_shift; }
+    a.contiguous = 1;   // marches may be long: every plane is reachable through the table
+    return flood_launch_common(a, f, z0, z1, k, st);
+}
+
+static int flood_launch_common(FloodArgs& a, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st) {
+    const uint32_t n = f.n, T = z1 - z0;
+    const bool fin = a.sdf != nullptr;
+    a.key_k0 = 0u - a.key_base * 16u;
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
     a.neg_zero = -0.0f;
     a.glut = jfa_lut_launch(f, st);
     if (!a.glut) return VPB_ERR_CUDA;
-    const ptrdiff_t kp = (ptrdiff_t)k * n * n;
-    a.contiguous = (above == mid + kp) && (below == mid - kp);
     const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
     a.lz = a.contiguous ? (cz < VPB_FLOOD_LZ ? cz : VPB_FLOOD_LZ) : 1;
     a.segs_z = (cz + a.lz - 1) / a.lz;
@@ -468,7 +510,6 @@ int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint
     }
     dim3 grid(n / SEG, grid_y, res_z * a.segs_z);
     VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
-    const bool fin = sdf != nullptr;
     switch (k >= 64 ? 64 : (int)k) {
         case 64: return launch_ss<64>(a, grid, fin, st);
         case 32: return launch_ss<32>(a, grid, fin, st);

@@ -114,6 +114,16 @@ VPB_API int vpb_jfa_pass_dev(const uint32_t* src_below, const uint32_t* src_mid,
                              uint32_t* dst_slab, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float voxel_size,
                              const float origin[3], const uint32_t* words_full, float* sdf_slab, uint32_t* seeds_slab,
                              void* stream);
+/* The same pass for multi-GPU runs WITHOUT halo copies: slab_states[r] (r < world <= 8) is the device address, valid in
+ * THIS process, of rank r's slab of the source state (planes [r*slab_planes, (r+1)*slab_planes), slab_planes*world == N)
+ * — the ranks' buffers mapped over NVLink (CUDA IPC / torch symmetric memory).  The kernel loads the planes z-k / z+k
+ * it needs straight from the owning GPU while it computes; the caller only has to barrier between passes.
+ * Replaces nothing in the reference (it has no multi-GPU path); returns VPB_ERR_ARG for shapes or
+ * frames the key-based kernel does not cover (N % 64, k not a power of two, degenerate frame): use vpb_jfa_pass_dev then. */
+VPB_API int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes,
+                                  uint32_t* dst_slab, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float voxel_size,
+                                  const float origin[3], const uint32_t* words_full, float* sdf_slab,
+                                  uint32_t* seeds_slab, void* stream);
 /* state -> sdf without a flood pass (N == 1, or callers that ran the passes themselves). */
 VPB_API int vpb_jfa_finalize_dev(const uint32_t* state_slab, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
                                  const float origin[3], const uint32_t* words_full, float* sdf_slab,

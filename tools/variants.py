@@ -8,9 +8,10 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "cuda_mesh_voxelization_b200", "build", "variants")
 VARIANTS = {
     "base": [],
-    "mb3": ["-DVPB_MARCH_MINBLOCKS=3"],
-    "pmov": ["-DVPB_PRED_MOV=1"],
-    "pmov_mb3": ["-DVPB_PRED_MOV=1", "-DVPB_MARCH_MINBLOCKS=3"],
+    "mb2": ["-DVPB_FLOOD_MINBLOCKS=2"],
+    "mb4": ["-DVPB_FLOOD_MINBLOCKS=4"],
+    "lz64": ["-DVPB_FLOOD_LZ=64"],
+    "mb4_lz64": ["-DVPB_FLOOD_MINBLOCKS=4", "-DVPB_FLOOD_LZ=64"],
 }
 if sys.argv[1] == "build":
     from cuda_mesh_voxelization_b200 import _build
