@@ -448,9 +448,12 @@ static bool flood_shape_ok(const Frame& f, uint32_t k, const void* dst, const vo
 
 static int flood_launch_common(FloodArgs& a, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st);
 
-int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
-                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
-                          uint32_t* seeds, cudaStream_t st) {
+bool jfa_frame_supports_keys(const Frame& f, uint32_t* key_base, float* bigz) { return frame_supports_keys(f, key_base, bigz); }
+
+// v3 entry (jfa_flood4.cu holds the dispatcher and the faster v4 pass; this one takes what v4 does not)
+int jfa_pass_flood3_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                           uint32_t* seeds, cudaStream_t st) {
     FloodArgs a;
     if (!flood_shape_ok(f, k, dst, sdf, seeds) || !frame_supports_keys(f, &a.key_base, &a.bigz))
         return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);

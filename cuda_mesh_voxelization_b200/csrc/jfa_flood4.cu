@@ -1,0 +1,447 @@
+// JFA flood pass v4 for sm_100a: the scatter + integer-key pass of jfa_flood.cu, re-cut to spend fewer issue slots per
+// voxel (the pass is issue-bound, not HBM-bound: profiles/r01_v3_flood_summary.txt, 249 thread-instructions per voxel).
+//
+// Same result as jfa_pass_gather / the reference (vplib/src/jfa/sequential.cpp:68-125, jfa/jfa.h:19-20), bit for bit.
+// What changed against v3 (jfa_flood.cu, kept for the shapes this file does not take and as a second witness in tests):
+//
+//  * A thread owns FOUR voxels: two x-adjacent voxels in two lattice-adjacent rows (y and y+k).  The two rows share
+//    8 of their 12 staged candidates per plane, so per plane a thread loads 12 entries (instead of 18) and computes
+//    the x part (sx-qx)^2 and the three z parts (sz-qz_t)^2 of an entry ONCE for both rows; only (sy-qy)^2, the two
+//    additions of the reference's ((dx*dx)+(dy*dy))+(dz*dz) and the key are per (voxel, candidate).
+//    Core cost: 99 instructions per voxel per pass instead of 150 (DESIGN.md section 4 has the count).
+//  * The staged plane has compile-time geometry (rows x window), so every shared-memory operand is base + immediate.
+//  * Staging converts two states at a time (LDG.64 / STS.64).
+//  * Tiles are 16 lattice rows x 64 voxels (8 warps): 12.5 % halo rows instead of 25 %.
+// Keys, scan order, tie handling, "no seed" sentinel and the packed FADD2/FFMA2 arithmetic are v3's (see there).
+#include "common.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace vpb {
+
+const float* jfa_lut_launch(const Frame& f, cudaStream_t st);                       // jfa.cu
+bool jfa_frame_supports_keys(const Frame& f, uint32_t* key_base, float* bigz);      // jfa_flood.cu
+int jfa_pass_flood3_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                           uint32_t* seeds, cudaStream_t st);                        // jfa_flood.cu (v3)
+
+namespace {
+
+#ifndef VPB_F4_LZ
+#define VPB_F4_LZ 64
+#endif
+#ifndef VPB_F4_MINBLOCKS
+#define VPB_F4_MINBLOCKS 2
+#endif
+
+constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
+constexpr int MAXN = 1024;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t OWN_CODE = 5;   // (dy,dx) code of the centre: row 1, column 1
+
+struct F4Args {
+    const uint32_t* src[3];   // below / mid / above (see vpb_jfa_pass_dev)
+    uint32_t* dst;
+    const uint32_t* words;    // occupancy (FINAL only)
+    float* sdf;               // FINAL only
+    uint32_t* seeds;          // FINAL only, optional
+    const float* glut;        // px | py | pz, 3 * MAXN floats
+    uint32_t n, z0, T;
+    int k;
+    int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
+    int lz, segs_z;           // outputs per march segment, segments per z-lattice column
+    int tiles_y;              // TR-row tiles per y-lattice column
+    uint32_t key_base;        // bits subtracted from every distance: (E0 << 23)
+    uint32_t key_k0;          // -(key_base * 16) mod 2^32
+    float bigz;               // z coordinate staged for "no seed"
+    float neg_zero;           // -0.0f, deliberately a RUNTIME value: see sq2() in jfa_tiled.cu
+};
+
+template <int SS, int TR>
+struct Cfg {
+    static constexpr int NW = TR / 2;                 // warps per CTA: one per pair of lattice rows
+    static constexpr int THREADS = NW * 32;
+    static constexpr int W = SEG + 2 * SS;            // staged window per row (SS = 64: three 64-wide segments)
+    static constexpr int ROWS = TR + 2;
+    static constexpr int PW = ROWS * W;               // entries per staged plane
+    static constexpr bool ALIGNED = (SS % 2) == 0;    // staged/evaluated in aligned pairs
+    static constexpr int G = ALIGNED ? 2 : 1;         // entries per staging item
+    static constexpr int ITEMS = PW / G;
+    static constexpr int NP = (ITEMS + THREADS - 1) / THREADS;
+    static constexpr int NBUF = SS >= 64 ? 1 : 2;     // float planes double-buffered unless the window is 192 wide
+    static constexpr size_t SMEM = ((size_t)3 * MAXN + (size_t)NBUF * 3 * PW + (size_t)4 * PW) * 4;
+};
+
+__device__ __forceinline__ float2 sq2(float2 x, float2 nz) { return __ffma2_rn(x, x, nz); }
+__device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
+
+// running winner of one output plane for the thread's 2 rows x 2 voxels
+struct Acc {
+    uint32_t key[2][2];
+    uint32_t tag[2][2];   // ring-slot word offset of the plane the winner came from
+};
+
+template <int SS, int TR, bool FINAL>
+struct Flood4 {
+    using C = Cfg<SS, TR>;
+
+    static __device__ __forceinline__ int gx_of(int i, int xs, int k) {
+        return (SS < 64) ? (xs - SS + i) : (xs + (i / SEG - 1) * k + (i % SEG));
+    }
+
+    // the three candidate columns of one staged row, for the thread's two x-adjacent voxels
+    static __device__ __forceinline__ void load_row(const float* p, float2 (&o)[3]) {
+        if (C::ALIGNED) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = *reinterpret_cast<const float2*>(p + c * SS);
+        } else {   // SS == 1: entries x0-1 .. x0+2
+            const float2 a = *reinterpret_cast<const float2*>(p);
+            const float2 b = *reinterpret_cast<const float2*>(p + 2);
+            o[0] = a; o[1] = make_float2(a.y, b.x); o[2] = b;
+        }
+    }
+
+    static __device__ __forceinline__ void merge(uint32_t& key, uint32_t& tag, uint32_t cand, uint32_t cand_tag) {
+        const bool win = (cand | 15u) < key;          // strictly smaller distance: later candidates lose ties
+        key = win ? cand : key;
+        tag = win ? cand_tag : tag;
+    }
+
+    static __device__ __forceinline__ void run(const F4Args& a) {
+        extern __shared__ float sm[];
+        const int n = (int)a.n, k = a.k;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float* const lut = sm;                                     // px | py | pz
+        float* const fbuf = sm + 3 * MAXN;                         // NBUF x (fx | fy | fz) planes
+        uint32_t* const ring = reinterpret_cast<uint32_t*>(fbuf + C::NBUF * 3 * C::PW);   // 4 packed planes
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(a.glut);
+            float4* s4 = reinterpret_cast<float4*>(lut);
+            for (int i = threadIdx.x; i < 3 * MAXN / 4; i += C::THREADS) s4[i] = __ldg(g4 + i);
+        }
+        // ---- tile coordinates ---------------------------------------------------------------------------------
+        const int xs = blockIdx.x * SEG;
+        const int rz = blockIdx.z / a.segs_z, sz = blockIdx.z - rz * a.segs_z;
+        const int zl0 = rz + sz * a.lz * k;                       // slab-local z of the first output plane
+        int steps = 0;
+        if (zl0 < (int)a.T) steps = min(a.lz, ((int)a.T - zl0 + k - 1) / k);
+        if (steps == 0) return;
+        const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
+        const int gy0 = ry + (ty * TR + 2 * warp) * k;             // the thread's rows: gy0 and gy0 + k
+        const bool ok[2] = {gy0 < n, gy0 + k < n};
+        // ---- what this thread stages (plane-invariant): in-plane voxel offset, -1 = outside the grid, -2 = nothing
+        int soff[C::NP];
+#pragma unroll
+        for (int v = 0; v < C::NP; ++v) {
+            const int e = ((int)threadIdx.x + C::THREADS * v) * C::G;
+            soff[v] = -2;
+            if (e < C::PW) {
+                const int row = e / C::W, i = e - row * C::W;
+                const int hy = ry + (ty * TR + row - 1) * k;
+                const int gx = gx_of(i, xs, k);
+                soff[v] = (hy >= 0 && hy < n && gx >= 0 && gx < n) ? hy * n + gx : -1;
+            }
+        }
+        __syncthreads();                                           // LUT visible
+        const size_t plane_sz = (size_t)n * n;
+        const int x0 = xs + 2 * lane;
+        const float2 nqx = make_float2(-lut[x0], -lut[x0 + 1]);
+        float2 nqy[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float q = ok[r] ? lut[MAXN + gy0 + r * k] : 0.0f;
+            nqy[r] = make_float2(-q, -q);
+        }
+        const float2 nz = make_float2(a.neg_zero, a.neg_zero);
+        const int tbase = 2 * warp * C::W + 2 * lane;              // candidate (rho, c) of this thread: tbase + rho*W + c*SS
+
+        uint32_t stq[C::NP][C::G];
+        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
+        auto fetch = [&](int p) {
+            const int zl = zl0 + p * k;
+            const uint32_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
+                                              : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
+#pragma unroll
+            for (int v = 0; v < C::NP; ++v) {
+                if (C::ALIGNED) {
+                    uint2 t = make_uint2(0u, 0u);
+                    if (soff[v] >= 0) t = __ldg(reinterpret_cast<const uint2*>(pp + soff[v]));
+                    stq[v][0] = t.x; stq[v][C::G - 1] = t.y;
+                } else {
+                    stq[v][0] = soff[v] >= 0 ? __ldg(pp + soff[v]) : 0u;
+                }
+            }
+        };
+        auto conv = [&](uint32_t s, float& x, float& y, float& z) {
+            const char* l = reinterpret_cast<const char*>(lut);
+            x = *reinterpret_cast<const float*>(l + (s & 0xFFCu));
+            y = *reinterpret_cast<const float*>(l + 4 * MAXN + ((s >> 10) & 0xFFCu));
+            const float zz = *reinterpret_cast<const float*>(l + 8 * MAXN + ((s >> 20) & 0xFFCu));
+            z = s ? zz : a.bigz;
+        };
+        auto stage = [&](int p) {
+            float* f = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW;
+            uint32_t* ps = ring + ((p + 1) & 3) * C::PW;
+#pragma unroll
+            for (int v = 0; v < C::NP; ++v) {
+                if (soff[v] == -2) continue;
+                const int e = ((int)threadIdx.x + C::THREADS * v) * C::G;
+                if (C::ALIGNED) {
+                    float2 x, y, z;
+                    conv(stq[v][0], x.x, y.x, z.x);
+                    conv(stq[v][C::G - 1], x.y, y.y, z.y);
+                    *reinterpret_cast<float2*>(f + e) = x;
+                    *reinterpret_cast<float2*>(f + C::PW + e) = y;
+                    *reinterpret_cast<float2*>(f + 2 * C::PW + e) = z;
+                    *reinterpret_cast<uint2*>(ps + e) = make_uint2(stq[v][0], stq[v][C::G - 1]);
+                } else {
+                    float x, y, z;
+                    conv(stq[v][0], x, y, z);
+                    f[e] = x; f[C::PW + e] = y; f[2 * C::PW + e] = z;
+                    ps[e] = stq[v][0];
+                }
+            }
+        };
+
+        Acc acc[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { acc[s].key[r][0] = acc[s].key[r][1] = NONE; acc[s].tag[r][0] = acc[s].tag[r][1] = 0u; }
+
+        // one input plane p: candidates dz=-1 of output p+1 (accN), dz=0 of output p (accC), dz=+1 of output p-1 (accP),
+        // then output p-1 is complete and written.
+        auto step = [&](int p, Acc& accN, Acc& accC, Acc& accP) {
+            const bool in_grid = plane_in_grid(p);
+            if (ok[0] && in_grid) {
+                const float* fb = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW + tbase;
+                const uint32_t tag = (uint32_t)(((p + 1) & 3) * C::PW);
+                const int zN = min(max(zl0 + (p + 1) * k + (int)a.z0, 0), MAXN - 1);
+                const int zC = min(max(zl0 + p * k + (int)a.z0, 0), MAXN - 1);
+                const int zP = min(max(zl0 + (p - 1) * k + (int)a.z0, 0), MAXN - 1);
+                const float qn = -lut[2 * MAXN + zN], qc = -lut[2 * MAXN + zC], qp = -lut[2 * MAXN + zP];
+                const float2 nq[3] = {make_float2(qn, qn), make_float2(qc, qc), make_float2(qp, qp)};
+                uint32_t g[2][3][2], carry[2][3][2], ownk[2][2];   // [row][target][voxel]
+#pragma unroll
+                for (int rho = 0; rho < 4; ++rho) {
+                    float2 fx[3], fy[3], fz[3];
+                    load_row(fb + rho * C::W, fx);
+                    load_row(fb + C::PW + rho * C::W, fy);
+                    load_row(fb + 2 * C::PW + rho * C::W, fz);
+                    uint32_t kk[2][3][3][2];   // [row][target][column][voxel]
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float2 X = sq2(__fadd2_rn(fx[c], nqx), nz);          // (sx - qx)^2, shared by both rows
+                        float2 Z[3];
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) Z[t] = sq2(__fadd2_rn(fz[c], nq[t]), nz);   // shared by both rows
+#pragma unroll
+                        for (int r2 = 0; r2 < 2; ++r2) {
+                            const int r = rho - r2;                 // candidate row relative to voxel row r2
+                            if (r < 0 || r > 2) continue;
+                            const float2 xy = __fadd2_rn(X, sq2(__fadd2_rn(fy[c], nqy[r2]), nz));
+                            const uint32_t kc = a.key_k0 + (uint32_t)(r * 4 + c);
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                const float2 d = __fadd2_rn(xy, Z[t]);   // ((dx*dx)+(dy*dy)) + (dz*dz)
+                                kk[r2][t][c][0] = __float_as_uint(d.x) * 16u + kc;
+                                kk[r2][t][c][1] = __float_as_uint(d.y) * 16u + kc;
+                                if (t == 1 && r == 1 && c == 1) {
+                                    // the voxel's own seed: scanned first by the reference.  Distance 0 (the voxel IS a
+                                    // seed) would wrap below the key base: give it the smallest key there is.
+                                    ownk[r2][0] = d.x == 0.0f ? OWN_CODE : kk[r2][t][c][0];
+                                    ownk[r2][1] = d.y == 0.0f ? OWN_CODE : kk[r2][t][c][1];
+                                }
+                            }
+                        }
+                    }
+                    // 9 (8 for the own plane) candidates per target reduce with four 3-input minima
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int r = rho - r2;
+                        if (r < 0 || r > 2) continue;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                uint32_t(&q)[3][2] = kk[r2][t];
+                                uint32_t& gg = g[r2][t][v];
+                                if (r == 0) {
+                                    gg = min3(q[0][v], q[1][v], q[2][v]);
+                                } else if (r == 1) {
+                                    if (t == 1) {
+                                        gg = min3(gg, q[0][v], q[2][v]);
+                                    } else {
+                                        gg = min3(gg, q[0][v], q[1][v]);
+                                        carry[r2][t][v] = q[2][v];
+                                    }
+                                } else {
+                                    if (t == 1) {
+                                        gg = min3(gg, q[0][v], q[1][v]);
+                                        gg = min(gg, q[2][v]);
+                                    } else {
+                                        gg = min3(gg, carry[r2][t][v], q[0][v]);
+                                        gg = min3(gg, q[1][v], q[2][v]);
+                                    }
+                                }
+                            }
+                    }
+                }
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        // output p+1: this plane is its first group
+                        accN.key[r2][v] = g[r2][0][v];
+                        accN.tag[r2][v] = tag;
+                        // output p: own seed first (keeps ties against the dz=-1 group), then this plane's 8 neighbours
+                        {
+                            const bool prev_wins = (accC.key[r2][v] | 15u) < ownk[r2][v];
+                            accC.key[r2][v] = prev_wins ? accC.key[r2][v] : ownk[r2][v];
+                            accC.tag[r2][v] = prev_wins ? accC.tag[r2][v] : tag;
+                        }
+                        merge(accC.key[r2][v], accC.tag[r2][v], g[r2][1][v], tag);
+                        // output p-1: last group
+                        merge(accP.key[r2][v], accP.tag[r2][v], g[r2][2][v], tag);
+                    }
+            } else if (ok[0]) {
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) accN.key[r2][0] = accN.key[r2][1] = NONE;   // no dz=-1 group for output p+1
+            }
+            // ---- output plane p-1 is complete ---------------------------------------------------------------------
+            if (p >= 1) {
+                const int zl = zl0 + (p - 1) * k;
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    if (!ok[r2]) continue;
+                    const int gy = gy0 + r2 * k;
+                    uint32_t s2[2];
+                    float d2[2];
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const uint32_t key = accP.key[r2][v];
+                        const uint32_t code = key & 15u;
+                        const uint32_t e = accP.tag[r2][v] + (uint32_t)(tbase + r2 * C::W + v) + (code >> 2) * C::W + (code & 3u) * SS;
+                        s2[v] = ring[e];
+                        if (FINAL) {
+                            const float d = (key >> 4) ? __uint_as_float((key >> 4) + a.key_base) : 0.0f;
+                            d2[v] = s2[v] ? d : INFINITY;
+                        }
+                    }
+                    const size_t vox = ((size_t)zl * n + gy) * n + x0;
+                    if (!FINAL) {
+                        *reinterpret_cast<uint2*>(a.dst + vox) = make_uint2(s2[0], s2[1]);
+                    } else {
+                        const size_t bit = ((size_t)(zl + a.z0) * n + gy) * n + x0;
+                        const uint32_t w = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
+                        *reinterpret_cast<float2*>(a.sdf + vox) = make_float2((w & 1u) ? d2[0] : -d2[0], (w & 2u) ? d2[1] : -d2[1]);
+                        if (a.seeds) *reinterpret_cast<uint2*>(a.seeds + vox) = make_uint2(jfa_public(s2[0]), jfa_public(s2[1]));
+                    }
+                }
+            }
+        };
+
+        // ---- march: planes p = -1 .. steps ------------------------------------------------------------------------
+        if (plane_in_grid(-1)) { fetch(-1); stage(-1); }
+        int p = -1;
+        auto iteration = [&](Acc& accN, Acc& accC, Acc& accP) {
+            __syncthreads();                                       // plane p staged by everyone (NBUF 2: plane p-1 consumed)
+            const bool more = p < steps && plane_in_grid(p + 1);
+            if (more) fetch(p + 1);
+            step(p, accN, accC, accP);
+            if (C::NBUF == 1) __syncthreads();                     // plane p consumed before it is overwritten
+            if (more) stage(p + 1);
+            ++p;
+        };
+#pragma unroll 1
+        while (true) {
+            // slot of output o is (o + 1) % 3; p = -1 + 3m here
+            iteration(acc[1], acc[0], acc[2]);
+            if (p > steps) break;
+            iteration(acc[2], acc[1], acc[0]);
+            if (p > steps) break;
+            iteration(acc[0], acc[2], acc[1]);
+            if (p > steps) break;
+        }
+    }
+};
+
+template <int SS, int TR, bool FINAL>
+__global__ void __launch_bounds__(Cfg<SS, TR>::THREADS, (TR == 16 ? VPB_F4_MINBLOCKS : 2 * VPB_F4_MINBLOCKS))
+jfa_pass_flood4(const F4Args a) { Flood4<SS, TR, FINAL>::run(a); }
+
+template <int SS, int TR, bool FINAL>
+int launch_one(const F4Args& a, dim3 grid, cudaStream_t st) {
+    using C = Cfg<SS, TR>;
+    static bool configured = false;
+    if (!configured) {
+        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_flood4<SS, TR, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    jfa_pass_flood4<SS, TR, FINAL><<<grid, C::THREADS, C::SMEM, st>>>(a);
+    VPB_LAUNCH_CHECK();
+    return VPB_OK;
+}
+
+template <int SS, int TR>
+int launch_ss(const F4Args& a, dim3 grid, bool fin, cudaStream_t st) {
+    return fin ? launch_one<SS, TR, true>(a, grid, st) : launch_one<SS, TR, false>(a, grid, st);
+}
+
+}  // namespace
+
+// Dispatcher of the key-based flood passes: v4 for N % 64 == 0, k a power of two with at least 8 lattice rows in y;
+// otherwise (and with VPB_JFA_KERNEL=flood3) v3, which itself falls back to the z-march / gather kernels.
+int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
+                          uint32_t* seeds, cudaStream_t st) {
+    const uint32_t n = f.n, T = z1 - z0;
+    const char* env = getenv("VPB_JFA_KERNEL");
+    const bool force3 = env && strcmp(env, "flood3") == 0;
+    const bool pow2 = (k & (k - 1)) == 0;
+    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
+    const int cy = (int)((n + k - 1) / k);                      // lattice points per y column
+    F4Args a;
+    if (force3 || n % SEG != 0 || n > MAXN || !pow2 || !align_ok || cy < 8 || !jfa_frame_supports_keys(f, &a.key_base, &a.bigz))
+        return jfa_pass_flood3_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    a.src[0] = below; a.src[1] = mid; a.src[2] = above;
+    a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
+    a.key_k0 = 0u - a.key_base * 16u;
+    a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
+    a.neg_zero = -0.0f;
+    a.glut = jfa_lut_launch(f, st);
+    if (!a.glut) return VPB_ERR_CUDA;
+    const ptrdiff_t kp = (ptrdiff_t)k * n * n;
+    a.contiguous = (above == mid + kp) && (below == mid - kp);
+    const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
+    a.lz = a.contiguous ? (cz < VPB_F4_LZ ? cz : VPB_F4_LZ) : 1;
+    a.segs_z = (cz + a.lz - 1) / a.lz;
+    const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
+    const int tr = cy >= 16 ? 16 : 8;
+    a.tiles_y = (cy + tr - 1) / tr;
+    dim3 grid(n / SEG, res_y * a.tiles_y, res_z * a.segs_z);
+    VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
+    const bool fin = sdf != nullptr;
+    if (tr == 8) {
+        switch (k >= 64 ? 64 : (int)k) {
+            case 64: return launch_ss<64, 8>(a, grid, fin, st);
+            case 32: return launch_ss<32, 8>(a, grid, fin, st);
+            case 16: return launch_ss<16, 8>(a, grid, fin, st);
+            case 8: return launch_ss<8, 8>(a, grid, fin, st);
+            default: break;   // k <= 4 with fewer than 16 lattice rows would need N < 64
+        }
+        return jfa_pass_flood3_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    }
+    switch (k >= 64 ? 64 : (int)k) {
+        case 64: return launch_ss<64, 16>(a, grid, fin, st);
+        case 32: return launch_ss<32, 16>(a, grid, fin, st);
+        case 16: return launch_ss<16, 16>(a, grid, fin, st);
+        case 8: return launch_ss<8, 16>(a, grid, fin, st);
+        case 4: return launch_ss<4, 16>(a, grid, fin, st);
+        case 2: return launch_ss<2, 16>(a, grid, fin, st);
+        default: return launch_ss<1, 16>(a, grid, fin, st);
+    }
+}
+
+}  // namespace vpb
