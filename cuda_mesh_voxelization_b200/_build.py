@@ -8,7 +8,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libvpb200.so")
-SOURCES = ["capi.cu", "vox.cu", "csg.cu", "jfa.cu", "jfa_tiled.cu", "jfa_flood.cu", "jfa_flood4.cu"]
+SOURCES = ["capi.cu", "vox.cu", "csg.cu", "jfa.cu", "jfa_tiled.cu", "jfa_flood.cu", "jfa_flood4.cu", "jfa_lattice.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "vpb200.h")]
 
 NVCC_FLAGS = [

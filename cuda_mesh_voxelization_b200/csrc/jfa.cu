@@ -29,6 +29,9 @@ int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint
                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
                           uint32_t* seeds, cudaStream_t st);
 
+int jfa_pass_lattice_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+                            const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st);   // jfa_lattice.cu
+
 namespace {
 
 constexpr int MAX_N = 1024;
@@ -252,6 +255,11 @@ int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* 
         return jfa_pass_gather_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
     if (env && strcmp(env, "march") == 0)
         return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    if (!env && !sdf) {
+        // first passes (<= 4 lattice points per axis): one thread per lattice, sparse candidates, HBM-bound
+        const int r = jfa_pass_lattice_launch(below, mid, above, dst, f, z0, z1, k, st);
+        if (r <= 0) return r;
+    }
     return jfa_pass_flood_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
 }
 

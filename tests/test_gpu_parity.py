@@ -211,6 +211,22 @@ def test_tiled_pass_equals_gather_pass_and_oracle(mesh, n, meshes, oracle, vpb, 
         assert np.array_equal(seeds_t, _public_seeds(oseeds, n))
 
 
+def test_lattice_first_passes_equal_flood_passes_512(meshes, oracle, vpb, monkeypatch):
+    """jfa_lattice.cu takes the k >= N/4 passes; with VPB_JFA_LATTICE=0 the flood kernels run them.  Same SDF and same
+    nearest seeds at 512^3 on the 1 348 128-face bunny (config 3), where the CPU oracle is too slow to ask."""
+    from cuda_mesh_voxelization_b200 import meshgen
+    v, t = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
+    n = 512
+    origin, vs = oracle.frame(v, n)
+    words = vpb.voxelize_host(v, t, n, vs, origin)
+    sdf_l, seeds_l = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_LATTICE", "0")
+    sdf_f, seeds_f = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_LATTICE")
+    assert np.array_equal(sdf_l.view(np.uint32), sdf_f.view(np.uint32))
+    assert np.array_equal(seeds_l, seeds_f)
+
+
 def test_tiled_pass_on_random_dense_ties(oracle, vpb):
     """Random occupancy at N=64/128: every pass is full of exact distance ties; scan order must decide identically."""
     for n, seed in [(64, 1), (128, 2)]:

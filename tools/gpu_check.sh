@@ -14,3 +14,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
 fi
+if [ "${NCUFULL:-0}" = "1" ]; then
+echo "== ncu --set full of the flood passes"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:jfa_pass_flood -c 10 -f -o gpurun_out/flood_full \
+    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+fi
