@@ -9,6 +9,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libvpb200.so")
 SOURCES = ["capi.cu", "vox.cu", "csg.cu", "jfa.cu", "jfa_tiled.cu", "jfa_flood.cu", "jfa_flood4.cu", "jfa_lattice.cu"]
+# compiled a second time with -DVPB_STATE64: the 64-bit seed state of grids above 1024^3 (csrc/common.cuh)
+SOURCES_S64 = ["jfa.cu", "jfa_flood4.cu", "jfa_lattice.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "vpb200.h")]
 
 NVCC_FLAGS = [
@@ -48,13 +50,13 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
-    for s in SOURCES:
+    for s, wide in [(s, False) for s in SOURCES] + [(s, True) for s in SOURCES_S64]:
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        obj = os.path.join(objdir, s.replace(".cu", "_s64.o" if wide else ".o"))
         objs.append(obj)
-        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
+        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, *extra_flags, *(["-DVPB_STATE64"] if wide else []), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

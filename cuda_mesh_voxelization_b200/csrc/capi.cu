@@ -72,19 +72,46 @@ int require_ready() {
 
 Frame make_frame(uint32_t n, float vs, const float origin[3]) { return Frame{origin[0], origin[1], origin[2], vs, n}; }
 
-// Runs seed extraction + all passes + signed output on one GPU.
-int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st) {
+// ---- state width dispatch: 32-bit words up to N = 1024, 64-bit up to 2048 (common.cuh) ----------------------------
+constexpr uint32_t kMaxJfaN = 2048;
+size_t state_size(uint32_t n) { return jfa_state64(n) ? 8 : 4; }
+int seed_any(const uint32_t* words, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st) {
+    return jfa_state64(n) ? jfa_seed_launch_s64(words, n, z0, z1, state, st) : jfa_seed_launch(words, n, z0, z1, state, st);
+}
+int pass_any(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f, uint32_t z0,
+             uint32_t z1, uint32_t k, const uint32_t* words, float* sdf, uint32_t* seeds, cudaStream_t st) {
+    return jfa_state64(f.n) ? jfa_pass_launch_s64(below, mid, above, dst, f, z0, z1, k, words, sdf, seeds, st)
+                            : jfa_pass_launch(below, mid, above, dst, f, z0, z1, k, words, sdf, seeds, st);
+}
+int finalize_any(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words, float* sdf,
+                 uint32_t* seeds, cudaStream_t st) {
+    return jfa_state64(f.n) ? jfa_finalize_launch_s64(state, f, z0, z1, words, sdf, seeds, st)
+                            : jfa_finalize_launch(state, f, z0, z1, words, sdf, seeds, st);
+}
+
+// Runs seed extraction + all passes + signed output on one GPU.  sdf may be NULL: the final pass never writes its
+// state destination, so the signed distance then goes INTO that free state buffer (4 B/voxel of HBM saved; at 2048^3
+// that is what makes the job fit one GPU) and *sdf_at tells the caller where it is.
+int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st,
+            float** sdf_at = nullptr) {
     const uint32_t n = f.n;
-    VPB_TRY(jfa_seed_launch(words, n, 0, n, sa, st));
-    const uint64_t plane = (uint64_t)n * n;
-    uint32_t* in = sa;
-    uint32_t* out = sb;
-    if (n / 2 == 0) return jfa_finalize_launch(in, f, 0, n, words, sdf, seeds, st);
+    VPB_TRY(seed_any(words, n, 0, n, sa, st));
+    const uint64_t plane_bytes = (uint64_t)n * n * state_size(n);
+    char* in = reinterpret_cast<char*>(sa);
+    char* out = reinterpret_cast<char*>(sb);
+    if (n / 2 == 0) {
+        float* target = sdf ? sdf : reinterpret_cast<float*>(out);
+        if (sdf_at) *sdf_at = target;
+        return finalize_any(sa, f, 0, n, words, target, seeds, st);
+    }
     for (uint32_t k = n / 2; k >= 1; k /= 2) {
         const bool last = (k == 1);
-        VPB_TRY(jfa_pass_launch(in - k * plane, in, in + k * plane, out, f, 0, n, k, words, last ? sdf : nullptr,
-                                last ? seeds : nullptr, st));
-        uint32_t* t = in; in = out; out = t;
+        float* target = sdf ? sdf : reinterpret_cast<float*>(out);
+        if (last && sdf_at) *sdf_at = target;
+        VPB_TRY(pass_any(reinterpret_cast<uint32_t*>(in - k * plane_bytes), reinterpret_cast<uint32_t*>(in),
+                         reinterpret_cast<uint32_t*>(in + k * plane_bytes), reinterpret_cast<uint32_t*>(out), f, 0, n, k, words,
+                         last ? target : nullptr, last ? seeds : nullptr, st));
+        char* t = in; in = out; out = t;
     }
     return VPB_OK;
 }
@@ -191,12 +218,12 @@ int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell, void* stre
 
 size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1) {
     if (z1 <= z0 || z1 > n) return 0;
-    return (size_t)n * n * (z1 - z0) * sizeof(uint32_t);
+    return (size_t)n * n * (z1 - z0) * state_size(n);
 }
 
 int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, void* stream) {
     VPB_TRY(require_ready());
-    return jfa_seed_launch(words_full, n, z0, z1, state, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+    return seed_any(words_full, n, z0, z1, state, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
 int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, uint32_t n,
@@ -204,8 +231,8 @@ int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t*
                      float* sdf, uint32_t* seeds, void* stream) {
     VPB_TRY(require_ready());
     VPB_REQUIRE(origin, "jfa_pass: null origin");
-    return jfa_pass_launch(below, mid, above, dst, make_frame(n, vs, origin), z0, z1, k, words_full, sdf, seeds,
-                           stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+    return pass_any(below, mid, above, dst, make_frame(n, vs, origin), z0, z1, k, words_full, sdf, seeds,
+                    stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
 int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes, uint32_t* dst,
@@ -214,6 +241,7 @@ int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, ui
     VPB_TRY(require_ready());
     VPB_REQUIRE(origin && slab_states && dst, "jfa_pass_peer: null argument");
     VPB_REQUIRE(n > 0 && n <= 1024 && z0 < z1 && z1 <= n && k >= 1 && k < n, "jfa_pass_peer: bad n=%u slab [%u,%u) k=%u", n, z0, z1, k);
+    VPB_REQUIRE(!jfa_state64(n), "jfa_pass_peer: the peer-memory pass only exists for the 32-bit state");
     VPB_REQUIRE(!sdf || words_full, "jfa_pass_peer: final pass needs the occupancy grid for the sign");
     return jfa_pass_flood_peer_launch(slab_states, world, slab_planes, dst, make_frame(n, vs, origin), z0, z1, k, words_full,
                                       sdf, seeds, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
@@ -223,15 +251,16 @@ int vpb_jfa_finalize_dev(const uint32_t* state, uint32_t n, uint32_t z0, uint32_
                          const uint32_t* words_full, float* sdf, uint32_t* seeds, void* stream) {
     VPB_TRY(require_ready());
     VPB_REQUIRE(origin, "jfa_finalize: null origin");
-    return jfa_finalize_launch(state, make_frame(n, vs, origin), z0, z1, words_full, sdf, seeds,
-                               stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+    return finalize_any(state, make_frame(n, vs, origin), z0, z1, words_full, sdf, seeds,
+                        stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
 int vpb_jfa_dev(const uint32_t* words, uint32_t n, float vs, const float origin[3], uint32_t* sa, uint32_t* sb,
                 float* sdf, uint32_t* seeds, void* stream) {
     VPB_TRY(require_ready());
     VPB_REQUIRE(words && sa && sb && sdf && origin, "jfa: null buffer");
-    VPB_REQUIRE(n > 0 && n <= 1024, "jfa: unsupported n=%u (32-bit state needs N <= 1024)", n);
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN, "jfa: unsupported n=%u (N <= %u)", n, kMaxJfaN);
+    VPB_REQUIRE(!seeds || n <= 1024, "jfa: the public 10-bit seed encoding needs N <= 1024");
     return jfa_run(words, make_frame(n, vs, origin), sa, sb, sdf, seeds, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
@@ -303,11 +332,11 @@ int vpb_csg_host(uint32_t* a, const uint32_t* b, uint32_t n, int op) {
     return finish_timing();
 }
 
+// two state buffers; the signed distance is written into whichever of them the final pass leaves free (jfa_run)
 static int reserve_jfa(uint32_t n, bool want_seeds) {
     const size_t vox = (size_t)n * n * n;
-    VPB_TRY(g_ctx.state_a.reserve(vox * 4));
-    VPB_TRY(g_ctx.state_b.reserve(vox * 4));
-    VPB_TRY(g_ctx.sdf.reserve(vox * 4));
+    VPB_TRY(g_ctx.state_a.reserve(vox * state_size(n)));
+    VPB_TRY(g_ctx.state_b.reserve(vox * state_size(n)));
     if (want_seeds) VPB_TRY(g_ctx.seeds.reserve(vox * 4));
     return VPB_OK;
 }
@@ -315,7 +344,8 @@ static int reserve_jfa(uint32_t n, bool want_seeds) {
 int vpb_jfa_host(const uint32_t* words, uint32_t n, float vs, const float origin[3], float* sdf_out, uint32_t* seeds_out) {
     VPB_TRY(require_ready());
     VPB_REQUIRE(words && sdf_out && origin, "jfa: null buffer");
-    VPB_REQUIRE(n > 0 && n <= 1024, "jfa: unsupported n=%u (32-bit state needs N <= 1024)", n);
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN, "jfa: unsupported n=%u (N <= %u)", n, kMaxJfaN);
+    VPB_REQUIRE(!seeds_out || n <= 1024, "jfa: the public 10-bit seed encoding needs N <= 1024");
     cudaStream_t st = g_ctx.stream;
     const uint64_t nw = grid_words(n);
     const size_t vox = (size_t)n * n * n;
@@ -324,10 +354,11 @@ int vpb_jfa_host(const uint32_t* words, uint32_t n, float vs, const float origin
     VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
     VPB_CUDA(cudaMemcpyAsync(g_ctx.grid_a.p, words, nw * 4, cudaMemcpyHostToDevice, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
+    float* sdf_dev = nullptr;
     VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), make_frame(n, vs, origin), g_ctx.state_a.as<uint32_t>(),
-                    g_ctx.state_b.as<uint32_t>(), g_ctx.sdf.as<float>(), seeds_out ? g_ctx.seeds.as<uint32_t>() : nullptr, st));
+                    g_ctx.state_b.as<uint32_t>(), nullptr, seeds_out ? g_ctx.seeds.as<uint32_t>() : nullptr, st, &sdf_dev));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
-    VPB_CUDA(cudaMemcpyAsync(sdf_out, g_ctx.sdf.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
     if (seeds_out) VPB_CUDA(cudaMemcpyAsync(seeds_out, g_ctx.seeds.p, vox * 4, cudaMemcpyDeviceToHost, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
     return finish_timing();
@@ -339,7 +370,7 @@ int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n
     VPB_TRY(require_ready());
     VPB_REQUIRE(n_meshes >= 1 && verts && n_verts && tris && n_tris && origin && n > 0, "pipeline: bad argument");
     VPB_REQUIRE(op >= VPB_OP_VOID && op <= VPB_OP_DIFFERENCE, "pipeline: bad op %d", op);
-    VPB_REQUIRE(!sdf_out || n <= 1024, "pipeline: sdf needs N <= 1024 (32-bit state)");
+    VPB_REQUIRE(!sdf_out || n <= kMaxJfaN, "pipeline: sdf needs N <= %u", kMaxJfaN);
     cudaStream_t st = g_ctx.stream;
     const uint64_t nw = grid_words(n);
     const size_t vox = (size_t)n * n * n;
@@ -362,12 +393,13 @@ int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n
         // apps/cli/main.cpp:126-186: fold into grids[0] for i > 0 when an operator is selected
         if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(g_ctx.grid_a.as<uint32_t>(), g_ctx.grid_b.as<uint32_t>(), nw, op, st));
     }
+    float* sdf_dev = nullptr;
     if (sdf_out)
         VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(),
-                        g_ctx.sdf.as<float>(), nullptr, st));
+                        nullptr, nullptr, st, &sdf_dev));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
     if (words_out) VPB_CUDA(cudaMemcpyAsync(words_out, g_ctx.grid_a.p, nw * 4, cudaMemcpyDeviceToHost, st));
-    if (sdf_out) VPB_CUDA(cudaMemcpyAsync(sdf_out, g_ctx.sdf.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    if (sdf_out) VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
     return finish_timing();
 }

@@ -47,17 +47,42 @@ static inline uint64_t grid_words(uint32_t n) { return words_for_bits((uint64_t)
 
 int num_sms();
 
-// ---- JFA state word (N <= 1024): bit0 = valid, x -> bits 2..11, y -> 12..21, z -> 22..31.
-// The fields sit where `(s >> shift) & 0xFFC` is directly the byte offset into a float table.
-// 0 = "no seed" (also what TMA / zero-fill produce outside the grid).
-__host__ __device__ __forceinline__ uint32_t jfa_pack(uint32_t x, uint32_t y, uint32_t z) {
+// ---- JFA state: the packed integer coordinates of a voxel's current nearest seed, 0 = "no seed" (also what zero-fill
+// produces outside the grid).  Two widths, chosen per translation unit (jfa.cu, jfa_flood4.cu and jfa_lattice.cu are
+// compiled twice, the second time with -DVPB_STATE64 and every exported name suffixed _s64):
+//   32-bit (N <= 1024): bit0 = valid, x -> bits 2..11, y -> 12..21, z -> 22..31
+//   64-bit (N <= 2048): low word bit0 = valid, x -> bits 2..12, y -> 13..23; high word z -> bits 2..12
+// The fields sit where `(word >> shift) & mask` is directly the BYTE offset into a float table of JFA_MAXN entries.
+#ifdef VPB_STATE64
+typedef uint64_t state_t;
+constexpr int JFA_MAXN = 2048;
+#define VPB_SFX(name) name##_s64
+__host__ __device__ __forceinline__ state_t jfa_pack(uint32_t x, uint32_t y, uint32_t z) {
+    return (state_t)(1u | (x << 2) | (y << 13)) | ((state_t)(z << 2) << 32);
+}
+__host__ __device__ __forceinline__ uint32_t jfa_offx(state_t s) { return (uint32_t)s & 0x1FFCu; }
+__host__ __device__ __forceinline__ uint32_t jfa_offy(state_t s) { return ((uint32_t)s >> 11) & 0x1FFCu; }
+__host__ __device__ __forceinline__ uint32_t jfa_offz(state_t s) { return (uint32_t)(s >> 32) & 0x1FFCu; }
+#else
+typedef uint32_t state_t;
+constexpr int JFA_MAXN = 1024;
+#define VPB_SFX(name) name
+__host__ __device__ __forceinline__ state_t jfa_pack(uint32_t x, uint32_t y, uint32_t z) {
     return 1u | (x << 2) | (y << 12) | (z << 22);
 }
-__host__ __device__ __forceinline__ uint32_t jfa_x(uint32_t s) { return (s >> 2) & 1023u; }
-__host__ __device__ __forceinline__ uint32_t jfa_y(uint32_t s) { return (s >> 12) & 1023u; }
-__host__ __device__ __forceinline__ uint32_t jfa_z(uint32_t s) { return s >> 22; }
-// public encoding of vpb200.h: x | y<<10 | z<<20, 0xFFFFFFFF = none
-__host__ __device__ __forceinline__ uint32_t jfa_public(uint32_t s) { return s ? (s >> 2) : 0xFFFFFFFFu; }
+__host__ __device__ __forceinline__ uint32_t jfa_offx(state_t s) { return s & 0xFFCu; }
+__host__ __device__ __forceinline__ uint32_t jfa_offy(state_t s) { return (s >> 10) & 0xFFCu; }
+__host__ __device__ __forceinline__ uint32_t jfa_offz(state_t s) { return (s >> 20) & 0xFFCu; }
+#endif
+__host__ __device__ __forceinline__ uint32_t jfa_x(state_t s) { return jfa_offx(s) >> 2; }
+__host__ __device__ __forceinline__ uint32_t jfa_y(state_t s) { return jfa_offy(s) >> 2; }
+__host__ __device__ __forceinline__ uint32_t jfa_z(state_t s) { return jfa_offz(s) >> 2; }
+// public encoding of vpb200.h: x | y<<10 | z<<20, 0xFFFFFFFF = none (callers only ask for it when N <= 1024)
+__host__ __device__ __forceinline__ uint32_t jfa_public(state_t s) {
+    return s ? (jfa_x(s) | (jfa_y(s) << 10) | (jfa_z(s) << 20)) : 0xFFFFFFFFu;
+}
+// which width a grid side uses: 64-bit above 1024, or everywhere with VPB_JFA_STATE64=1 (parity tests of the wide path)
+bool jfa_state64(uint32_t n);
 
 #ifdef __CUDACC__
 // ---- bit-grid helpers shared by the shell and seed kernels ----------------------------------------
@@ -100,5 +125,12 @@ int jfa_pass_flood_peer_launch(const uint32_t* const* slabs, uint32_t world, uin
                                float* sdf, uint32_t* seeds, cudaStream_t st);
 int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
                         float* sdf, uint32_t* seeds, cudaStream_t st);
+// the same three with the 64-bit state (N <= 2048); state pointers are uint64_t* behind the uint32_t* of the C ABI
+int jfa_seed_launch_s64(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
+int jfa_pass_launch_s64(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,
+                        uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
+                        cudaStream_t st);
+int jfa_finalize_launch_s64(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
+                            float* sdf, uint32_t* seeds, cudaStream_t st);
 
 }  // namespace vpb

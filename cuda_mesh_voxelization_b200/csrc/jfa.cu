@@ -22,26 +22,28 @@
 
 namespace vpb {
 
-int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
-                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
-                          uint32_t* seeds, cudaStream_t st);
+// This file is compiled twice: 32-bit state (N <= 1024) and, with -DVPB_STATE64, 64-bit state (N <= 2048, names + _s64).
+int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                                   const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                                   float* sdf, uint32_t* seeds, cudaStream_t st);                     // jfa_flood4.cu
+#ifndef VPB_STATE64
 int jfa_pass_tiled_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
                           uint32_t* seeds, cudaStream_t st);
-
-int jfa_pass_lattice_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
-                            const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st);   // jfa_lattice.cu
+#endif
+int VPB_SFX(jfa_pass_lattice_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                                     const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st);   // jfa_lattice.cu
 
 namespace {
 
-constexpr int MAX_N = 1024;
+constexpr int MAX_N = JFA_MAXN;
 
 // ---- seed extraction -------------------------------------------------------------------------------
 // N % 32 == 0: each lane derives the seed mask of one 32-voxel word from shifted row words, then the warp
 // writes the 32 words' states with coalesced 128-byte stores.
 __global__ void __launch_bounds__(256)
 jfa_seed_aligned(const uint32_t* __restrict__ words, uint32_t n, uint32_t z0, uint64_t slab_words,
-                 uint32_t* __restrict__ state) {
+                 state_t* __restrict__ state) {
     const uint32_t R = n / 32u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t first_word = (uint64_t)z0 * n * R;
@@ -49,7 +51,8 @@ jfa_seed_aligned(const uint32_t* __restrict__ words, uint32_t n, uint32_t z0, ui
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t w0 = warp * 32; w0 < slab_words; w0 += n_warps * 32) {
         const uint64_t wl = w0 + lane;  // slab-local word handled by this lane
-        uint32_t seed_mask = 0, base = 0;
+        uint32_t seed_mask = 0;
+        state_t base = 0;
         if (wl < slab_words) {
             const uint64_t w = first_word + wl;
             const uint32_t xw = (uint32_t)(w % R);
@@ -63,8 +66,8 @@ jfa_seed_aligned(const uint32_t* __restrict__ words, uint32_t n, uint32_t z0, ui
         const uint32_t lim = rem < 32 ? (uint32_t)rem : 32u;
         for (uint32_t i = 0; i < lim; ++i) {
             const uint32_t m = __shfl_sync(0xffffffffu, seed_mask, i);
-            const uint32_t b = __shfl_sync(0xffffffffu, base, i);
-            state[(w0 + i) * 32 + lane] = ((m >> lane) & 1u) ? (b + (lane << 2)) : 0u;
+            const state_t b = __shfl_sync(0xffffffffu, base, i);
+            state[(w0 + i) * 32 + lane] = ((m >> lane) & 1u) ? (b + (lane << 2)) : (state_t)0;
         }
     }
 }
@@ -72,10 +75,10 @@ jfa_seed_aligned(const uint32_t* __restrict__ words, uint32_t n, uint32_t z0, ui
 // any N: one thread per voxel, 26 bit probes for set voxels
 __global__ void __launch_bounds__(256)
 jfa_seed_generic(const uint32_t* __restrict__ words, uint32_t n, uint32_t z0, uint64_t slab_voxels,
-                 uint32_t* __restrict__ state) {
+                 state_t* __restrict__ state) {
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < slab_voxels; v += (uint64_t)gridDim.x * blockDim.x) {
         const int x = (int)(v % n), y = (int)((v / n) % n), z = (int)(v / ((uint64_t)n * n)) + (int)z0;
-        uint32_t s = 0;
+        state_t s = 0;
         if (bit_at(words, ((uint64_t)z * n + y) * n + x)) {
             bool interior = true;
             for (int dz = -1; dz <= 1 && interior; ++dz)
@@ -102,7 +105,7 @@ __device__ __forceinline__ void fill_tables(float* px, float* py, float* pz, con
 }
 
 // CalculateDistance(voxelPos, seedPos), jfa/jfa.h:19-20: ((dx*dx) + (dy*dy)) + (dz*dz), d = seed - voxel
-__device__ __forceinline__ float seed_distance(uint32_t s, const float* px, const float* py, const float* pz,
+__device__ __forceinline__ float seed_distance(state_t s, const float* px, const float* py, const float* pz,
                                                float qx, float qy, float qz) {
     const float dx = __fsub_rn(px[jfa_x(s)], qx);
     const float dy = __fsub_rn(py[jfa_y(s)], qy);
@@ -112,7 +115,7 @@ __device__ __forceinline__ float seed_distance(uint32_t s, const float* px, cons
 
 // sign convention of the reference: set voxels start at +INF / 0, unset ones at -INF (apps/cli/main.cpp:200,
 // jfa/sequential.cpp:56-59) and copysignf keeps it (sequential.cpp:108)
-__device__ __forceinline__ void write_result(uint32_t s, float d, bool inside, uint64_t v, float* __restrict__ sdf,
+__device__ __forceinline__ void write_result(state_t s, float d, bool inside, uint64_t v, float* __restrict__ sdf,
                                              uint32_t* __restrict__ seeds) {
     const float mag = s ? d : INFINITY;
     sdf[v] = inside ? mag : -mag;
@@ -121,8 +124,8 @@ __device__ __forceinline__ void write_result(uint32_t s, float d, bool inside, u
 
 template <bool FINAL>
 __global__ void __launch_bounds__(256)
-jfa_pass_gather(const uint32_t* __restrict__ below, const uint32_t* __restrict__ mid,
-                const uint32_t* __restrict__ above, uint32_t* __restrict__ dst, Frame f, uint32_t z0,
+jfa_pass_gather(const state_t* __restrict__ below, const state_t* __restrict__ mid,
+                const state_t* __restrict__ above, state_t* __restrict__ dst, Frame f, uint32_t z0,
                 uint64_t slab_voxels, int k, const uint32_t* __restrict__ words, float* __restrict__ sdf,
                 uint32_t* __restrict__ seeds) {
     __shared__ float px[MAX_N], py[MAX_N], pz[MAX_N];
@@ -134,24 +137,24 @@ jfa_pass_gather(const uint32_t* __restrict__ below, const uint32_t* __restrict__
         const int x = (int)(v % n), y = (int)((v / n) % n), zl = (int)(v / plane);
         const int z = zl + (int)z0;
         const float qx = px[x], qy = py[y], qz = pz[z];
-        uint32_t best_s = mid[v];
+        state_t best_s = mid[v];
         float best = best_s ? seed_distance(best_s, px, py, pz, qx, qy, qz) : INFINITY;
 #pragma unroll
         for (int dz = -1; dz <= 1; ++dz) {
             const int zz = z + dz * k;
             if (zz < 0 || zz >= n) continue;
-            const uint32_t* __restrict__ src = dz < 0 ? below : (dz == 0 ? mid : above);
+            const state_t* __restrict__ src = dz < 0 ? below : (dz == 0 ? mid : above);
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
                 const int yy = y + dy * k;
                 if (yy < 0 || yy >= n) continue;
-                const uint32_t* __restrict__ row = src + (uint64_t)zl * plane + (uint64_t)yy * n;
+                const state_t* __restrict__ row = src + (uint64_t)zl * plane + (uint64_t)yy * n;
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     if (dx == 0 && dy == 0 && dz == 0) continue;
                     const int xx = x + dx * k;
                     if (xx < 0 || xx >= n) continue;
-                    const uint32_t s = __ldg(row + xx);
+                    const state_t s = __ldg(row + xx);
                     if (!s) continue;
                     const float d = seed_distance(s, px, py, pz, qx, qy, qz);
                     if (d < best) { best = d; best_s = s; }
@@ -164,7 +167,7 @@ jfa_pass_gather(const uint32_t* __restrict__ below, const uint32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-jfa_finalize(const uint32_t* __restrict__ state, Frame f, uint32_t z0, uint64_t slab_voxels,
+jfa_finalize(const state_t* __restrict__ state, Frame f, uint32_t z0, uint64_t slab_voxels,
              const uint32_t* __restrict__ words, float* __restrict__ sdf, uint32_t* __restrict__ seeds) {
     __shared__ float px[MAX_N], py[MAX_N], pz[MAX_N];
     fill_tables(px, py, pz, f);
@@ -173,7 +176,7 @@ jfa_finalize(const uint32_t* __restrict__ state, Frame f, uint32_t z0, uint64_t 
     const uint64_t plane = (uint64_t)n * n;
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < slab_voxels; v += (uint64_t)gridDim.x * blockDim.x) {
         const int x = (int)(v % n), y = (int)((v / n) % n), z = (int)(v / plane) + (int)z0;
-        const uint32_t s = state[v];
+        const state_t s = state[v];
         const float d = s ? seed_distance(s, px, py, pz, px[x], py[y], pz[z]) : INFINITY;
         write_result(s, d, bit_at(words, (uint64_t)z * plane + (uint64_t)y * n + x), v, sdf, seeds);
     }
@@ -195,9 +198,9 @@ unsigned grid_for(uint64_t items) {
 
 }  // namespace
 
-// One 12 KB device buffer per process (the library serves one caller thread / one frame at a time, like vplib).
-// Rebuilt on every pass launch: 3 us, stream-ordered before the pass that reads it.
-const float* jfa_lut_launch(const Frame& f, cudaStream_t st) {
+// One 12 / 24 KB device buffer per process and state width (the library serves one caller thread / one frame at a time,
+// like vplib).  Rebuilt on every pass launch: 3 us, stream-ordered before the pass that reads it.
+const float* VPB_SFX(jfa_lut_launch)(const Frame& f, cudaStream_t st) {
     static float* lut = nullptr;
     static int lut_device = -1;
     int dev = 0;
@@ -216,9 +219,17 @@ const float* jfa_lut_launch(const Frame& f, cudaStream_t st) {
     return lut;
 }
 
-int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st) {
+#ifndef VPB_STATE64
+bool jfa_state64(uint32_t n) {
+    const char* env = getenv("VPB_JFA_STATE64");
+    return n > 1024u || (env && strcmp(env, "1") == 0);
+}
+#endif
+
+int VPB_SFX(jfa_seed_launch)(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state_, cudaStream_t st) {
+    state_t* state = reinterpret_cast<state_t*>(state_);
     VPB_REQUIRE(words_full && state, "jfa_seed: null buffer");
-    VPB_REQUIRE(n > 0 && n <= MAX_N && z0 < z1 && z1 <= n, "jfa_seed: unsupported n=%u slab [%u,%u) (32-bit state needs N <= 1024)", n, z0, z1);
+    VPB_REQUIRE(n > 0 && n <= MAX_N && z0 < z1 && z1 <= n, "jfa_seed: unsupported n=%u slab [%u,%u) (N <= %d)", n, z0, z1, MAX_N);
     const uint64_t slab_voxels = (uint64_t)n * n * (z1 - z0);
     if (n % 32u == 0) {
         const uint64_t slab_words = slab_voxels / 32;
@@ -230,9 +241,9 @@ int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_
     return VPB_OK;
 }
 
-int jfa_pass_gather_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
-                           const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
-                           float* sdf, uint32_t* seeds, cudaStream_t st) {
+int VPB_SFX(jfa_pass_gather_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                                    const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                                    float* sdf, uint32_t* seeds, cudaStream_t st) {
     const uint64_t slab_voxels = (uint64_t)f.n * f.n * (z1 - z0);
     if (sdf)
         jfa_pass_gather<true><<<grid_for(slab_voxels), 256, 0, st>>>(below, mid, above, dst, f, z0, slab_voxels, (int)k, words_full, sdf, seeds);
@@ -242,33 +253,41 @@ int jfa_pass_gather_launch(const uint32_t* below, const uint32_t* mid, const uin
     return VPB_OK;
 }
 
-int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,
-                    uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
-                    cudaStream_t st) {
+int VPB_SFX(jfa_pass_launch)(const uint32_t* below_, const uint32_t* mid_, const uint32_t* above_, uint32_t* dst_, const Frame& f,
+                             uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
+                             cudaStream_t st) {
+    const state_t* below = reinterpret_cast<const state_t*>(below_);
+    const state_t* mid = reinterpret_cast<const state_t*>(mid_);
+    const state_t* above = reinterpret_cast<const state_t*>(above_);
+    state_t* dst = reinterpret_cast<state_t*>(dst_);
     VPB_REQUIRE(mid && dst, "jfa_pass: null state");
     VPB_REQUIRE(f.n > 0 && f.n <= MAX_N && z0 < z1 && z1 <= f.n, "jfa_pass: unsupported n=%u slab [%u,%u)", f.n, z0, z1);
     VPB_REQUIRE(k >= 1 && k < f.n, "jfa_pass: bad step %u", k);
     VPB_REQUIRE(!sdf || words_full, "jfa_pass: final pass needs the occupancy grid for the sign");
+    VPB_REQUIRE(!seeds || f.n <= 1024, "jfa_pass: the public 10-bit seed encoding needs N <= 1024");
     // VPB_JFA_KERNEL=gather|march forces the straightforward / the register-cache kernel (tests compare all three)
     const char* env = getenv("VPB_JFA_KERNEL");
     if (env && strcmp(env, "gather") == 0)
-        return jfa_pass_gather_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+        return VPB_SFX(jfa_pass_gather_launch)(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+#ifndef VPB_STATE64
     if (env && strcmp(env, "march") == 0)
         return jfa_pass_tiled_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+#endif
     if (!env && !sdf) {
         // first passes (<= 4 lattice points per axis): one thread per lattice, sparse candidates, HBM-bound
-        const int r = jfa_pass_lattice_launch(below, mid, above, dst, f, z0, z1, k, st);
+        const int r = VPB_SFX(jfa_pass_lattice_launch)(below, mid, above, dst, f, z0, z1, k, st);
         if (r <= 0) return r;
     }
-    return jfa_pass_flood_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+    return VPB_SFX(jfa_pass_flood_launch)(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
 }
 
-int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
-                        float* sdf, uint32_t* seeds, cudaStream_t st) {
+int VPB_SFX(jfa_finalize_launch)(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
+                                 float* sdf, uint32_t* seeds, cudaStream_t st) {
     VPB_REQUIRE(state && words_full && sdf, "jfa_finalize: null buffer");
     VPB_REQUIRE(f.n > 0 && f.n <= MAX_N && z0 < z1 && z1 <= f.n, "jfa_finalize: unsupported n=%u slab [%u,%u)", f.n, z0, z1);
+    VPB_REQUIRE(!seeds || f.n <= 1024, "jfa_finalize: the public 10-bit seed encoding needs N <= 1024");
     const uint64_t slab_voxels = (uint64_t)f.n * f.n * (z1 - z0);
-    jfa_finalize<<<grid_for(slab_voxels), 256, 0, st>>>(state, f, z0, slab_voxels, words_full, sdf, seeds);
+    jfa_finalize<<<grid_for(slab_voxels), 256, 0, st>>>(reinterpret_cast<const state_t*>(state), f, z0, slab_voxels, words_full, sdf, seeds);
     VPB_LAUNCH_CHECK();
     return VPB_OK;
 }

@@ -20,11 +20,20 @@
 
 namespace vpb {
 
-const float* jfa_lut_launch(const Frame& f, cudaStream_t st);                       // jfa.cu
+// Compiled twice: 32-bit state (N <= 1024) and, with -DVPB_STATE64, 64-bit state (N <= 2048, names + _s64; common.cuh).
+const float* VPB_SFX(jfa_lut_launch)(const Frame& f, cudaStream_t st);              // jfa.cu
 bool jfa_frame_supports_keys(const Frame& f, uint32_t* key_base, float* bigz);      // jfa_flood.cu
+#ifndef VPB_STATE64
 int jfa_pass_flood3_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
                            const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
                            uint32_t* seeds, cudaStream_t st);                        // jfa_flood.cu (v3)
+#define VPB_F4_FALLBACK jfa_pass_flood3_launch
+#else
+int jfa_pass_gather_launch_s64(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                               const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                               float* sdf, uint32_t* seeds, cudaStream_t st);        // jfa.cu: the wide state has no v3 / z-march
+#define VPB_F4_FALLBACK jfa_pass_gather_launch_s64
+#endif
 
 namespace {
 
@@ -36,13 +45,13 @@ namespace {
 #endif
 
 constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
-constexpr int MAXN = 1024;
+constexpr int MAXN = JFA_MAXN;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t OWN_CODE = 5;   // (dy,dx) code of the centre: row 1, column 1
 
 struct F4Args {
-    const uint32_t* src[3];   // below / mid / above (see vpb_jfa_pass_dev)
-    uint32_t* dst;
+    const state_t* src[3];    // below / mid / above (see vpb_jfa_pass_dev)
+    state_t* dst;
     const uint32_t* words;    // occupancy (FINAL only)
     float* sdf;               // FINAL only
     uint32_t* seeds;          // FINAL only, optional
@@ -70,11 +79,21 @@ struct Cfg {
     static constexpr int ITEMS = PW / G;
     static constexpr int NP = (ITEMS + THREADS - 1) / THREADS;
     static constexpr int NBUF = SS >= 64 ? 1 : 2;     // float planes double-buffered unless the window is 192 wide
-    static constexpr size_t SMEM = ((size_t)3 * MAXN + (size_t)NBUF * 3 * PW + (size_t)4 * PW) * 4;
+    static constexpr size_t SMEM = ((size_t)3 * MAXN + (size_t)NBUF * 3 * PW) * 4 + (size_t)4 * PW * sizeof(state_t);
 };
 
 __device__ __forceinline__ float2 sq2(float2 x, float2 nz) { return __ffma2_rn(x, x, nz); }
 __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u32(a, b, c); }
+
+// two x-adjacent states with one vector access (the pair is aligned: even x, N % 64 == 0)
+__device__ __forceinline__ void ldg_pair(const uint32_t* p, uint32_t& a, uint32_t& b) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p)); a = t.x; b = t.y;
+}
+__device__ __forceinline__ void ldg_pair(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(p)); a = t.x; b = t.y;
+}
+__device__ __forceinline__ void st_pair(uint32_t* p, uint32_t a, uint32_t b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
+__device__ __forceinline__ void st_pair(uint64_t* p, uint64_t a, uint64_t b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
 
 // running winner of one output plane for the thread's 2 rows x 2 voxels
 struct Acc {
@@ -109,12 +128,12 @@ struct Flood4 {
     }
 
     static __device__ __forceinline__ void run(const F4Args& a) {
-        extern __shared__ float sm[];
+        extern __shared__ __align__(16) float sm[];
         const int n = (int)a.n, k = a.k;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float* const lut = sm;                                     // px | py | pz
         float* const fbuf = sm + 3 * MAXN;                         // NBUF x (fx | fy | fz) planes
-        uint32_t* const ring = reinterpret_cast<uint32_t*>(fbuf + C::NBUF * 3 * C::PW);   // 4 packed planes
+        state_t* const ring = reinterpret_cast<state_t*>(fbuf + C::NBUF * 3 * C::PW);     // 4 packed planes
         {
             const float4* g4 = reinterpret_cast<const float4*>(a.glut);
             float4* s4 = reinterpret_cast<float4*>(lut);
@@ -156,33 +175,32 @@ struct Flood4 {
         const float2 nz = make_float2(a.neg_zero, a.neg_zero);
         const int tbase = 2 * warp * C::W + 2 * lane;              // candidate (rho, c) of this thread: tbase + rho*W + c*SS
 
-        uint32_t stq[C::NP][C::G];
+        state_t stq[C::NP][C::G];
         auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
         auto fetch = [&](int p) {
             const int zl = zl0 + p * k;
-            const uint32_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
+            const state_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
                                               : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
 #pragma unroll
             for (int v = 0; v < C::NP; ++v) {
                 if (C::ALIGNED) {
-                    uint2 t = make_uint2(0u, 0u);
-                    if (soff[v] >= 0) t = __ldg(reinterpret_cast<const uint2*>(pp + soff[v]));
-                    stq[v][0] = t.x; stq[v][C::G - 1] = t.y;
+                    stq[v][0] = stq[v][C::G - 1] = 0;
+                    if (soff[v] >= 0) ldg_pair(pp + soff[v], stq[v][0], stq[v][C::G - 1]);
                 } else {
-                    stq[v][0] = soff[v] >= 0 ? __ldg(pp + soff[v]) : 0u;
+                    stq[v][0] = soff[v] >= 0 ? __ldg(pp + soff[v]) : (state_t)0;
                 }
             }
         };
-        auto conv = [&](uint32_t s, float& x, float& y, float& z) {
+        auto conv = [&](state_t s, float& x, float& y, float& z) {
             const char* l = reinterpret_cast<const char*>(lut);
-            x = *reinterpret_cast<const float*>(l + (s & 0xFFCu));
-            y = *reinterpret_cast<const float*>(l + 4 * MAXN + ((s >> 10) & 0xFFCu));
-            const float zz = *reinterpret_cast<const float*>(l + 8 * MAXN + ((s >> 20) & 0xFFCu));
+            x = *reinterpret_cast<const float*>(l + jfa_offx(s));
+            y = *reinterpret_cast<const float*>(l + 4 * MAXN + jfa_offy(s));
+            const float zz = *reinterpret_cast<const float*>(l + 8 * MAXN + jfa_offz(s));
             z = s ? zz : a.bigz;
         };
         auto stage = [&](int p) {
             float* f = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW;
-            uint32_t* ps = ring + ((p + 1) & 3) * C::PW;
+            state_t* ps = ring + ((p + 1) & 3) * C::PW;
 #pragma unroll
             for (int v = 0; v < C::NP; ++v) {
                 if (soff[v] == -2) continue;
@@ -194,7 +212,7 @@ struct Flood4 {
                     *reinterpret_cast<float2*>(f + e) = x;
                     *reinterpret_cast<float2*>(f + C::PW + e) = y;
                     *reinterpret_cast<float2*>(f + 2 * C::PW + e) = z;
-                    *reinterpret_cast<uint2*>(ps + e) = make_uint2(stq[v][0], stq[v][C::G - 1]);
+                    st_pair(ps + e, stq[v][0], stq[v][C::G - 1]);
                 } else {
                     float x, y, z;
                     conv(stq[v][0], x, y, z);
@@ -316,7 +334,7 @@ struct Flood4 {
                 for (int r2 = 0; r2 < 2; ++r2) {
                     if (!ok[r2]) continue;
                     const int gy = gy0 + r2 * k;
-                    uint32_t s2[2];
+                    state_t s2[2];
                     float d2[2];
 #pragma unroll
                     for (int v = 0; v < 2; ++v) {
@@ -331,7 +349,7 @@ struct Flood4 {
                     }
                     const size_t vox = ((size_t)zl * n + gy) * n + x0;
                     if (!FINAL) {
-                        *reinterpret_cast<uint2*>(a.dst + vox) = make_uint2(s2[0], s2[1]);
+                        st_pair(a.dst + vox, s2[0], s2[1]);
                     } else {
                         const size_t bit = ((size_t)(zl + a.z0) * n + gy) * n + x0;
                         const uint32_t w = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
@@ -393,24 +411,25 @@ int launch_ss(const F4Args& a, dim3 grid, bool fin, cudaStream_t st) {
 
 // Dispatcher of the key-based flood passes: v4 for N % 64 == 0, k a power of two with at least 8 lattice rows in y;
 // otherwise (and with VPB_JFA_KERNEL=flood3) v3, which itself falls back to the z-march / gather kernels.
-int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
-                          const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf,
-                          uint32_t* seeds, cudaStream_t st) {
+int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                                   const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                                   float* sdf, uint32_t* seeds, cudaStream_t st) {
     const uint32_t n = f.n, T = z1 - z0;
     const char* env = getenv("VPB_JFA_KERNEL");
     const bool force3 = env && strcmp(env, "flood3") == 0;
     const bool pow2 = (k & (k - 1)) == 0;
-    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
+    const bool align_ok = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(mid)) & (2 * sizeof(state_t) - 1)) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(seeds)) & 7u) == 0;
     const int cy = (int)((n + k - 1) / k);                      // lattice points per y column
     F4Args a;
     if (force3 || n % SEG != 0 || n > MAXN || !pow2 || !align_ok || cy < 8 || !jfa_frame_supports_keys(f, &a.key_base, &a.bigz))
-        return jfa_pass_flood3_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+        return VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
     a.src[0] = below; a.src[1] = mid; a.src[2] = above;
     a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
     a.key_k0 = 0u - a.key_base * 16u;
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
     a.neg_zero = -0.0f;
-    a.glut = jfa_lut_launch(f, st);
+    a.glut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.glut) return VPB_ERR_CUDA;
     const ptrdiff_t kp = (ptrdiff_t)k * n * n;
     a.contiguous = (above == mid + kp) && (below == mid - kp);
@@ -431,7 +450,7 @@ int jfa_pass_flood_launch(const uint32_t* below, const uint32_t* mid, const uint
             case 8: return launch_ss<8, 8>(a, grid, fin, st);
             default: break;   // k <= 4 with fewer than 16 lattice rows would need N < 64
         }
-        return jfa_pass_flood3_launch(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+        return VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
     }
     switch (k >= 64 ? 64 : (int)k) {
         case 64: return launch_ss<64, 16>(a, grid, fin, st);

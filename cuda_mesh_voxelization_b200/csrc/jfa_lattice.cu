@@ -25,16 +25,17 @@
 
 namespace vpb {
 
-const float* jfa_lut_launch(const Frame& f, cudaStream_t st);   // jfa.cu: px | py | pz, 3 * 1024 floats
+// compiled twice: 32-bit state and, with -DVPB_STATE64, 64-bit state (names + _s64), see common.cuh
+const float* VPB_SFX(jfa_lut_launch)(const Frame& f, cudaStream_t st);   // jfa.cu: px | py | pz, 3 * JFA_MAXN floats
 
 namespace {
 
-constexpr int MAXN = 1024;
+constexpr int MAXN = JFA_MAXN;
 constexpr int TX = 32, TY = 4, THREADS = TX * TY;
 
 struct LatArgs {
-    const uint32_t* src[3];   // below / mid / above (see vpb_jfa_pass_dev)
-    uint32_t* dst;
+    const state_t* src[3];    // below / mid / above (see vpb_jfa_pass_dev)
+    state_t* dst;
     const float* lut;
     int n, z0, T, k;
     int contiguous;           // src[0] == src[1] - k planes and src[2] == src[1] + k planes
@@ -51,7 +52,7 @@ template <int L, bool LUT_SMEM>
 __global__ void __launch_bounds__(THREADS)
 jfa_pass_lattice(const LatArgs a) {
     constexpr int PTS = L * L;                 // points per lattice plane
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     const float* lut = a.lut;
     uint32_t* base = smem;
     if (LUT_SMEM) {
@@ -65,9 +66,9 @@ jfa_pass_lattice(const LatArgs a) {
     }
     auto ld = [&](int idx) -> float { return LUT_SMEM ? lut[idx] : __ldg(lut + idx); };
     const int tid = threadIdx.y * TX + threadIdx.x;
-    uint32_t* const src_pl = base + tid;                                    // [PTS][THREADS]
-    float* const bD = reinterpret_cast<float*>(base + PTS * THREADS) + tid; // [3][PTS][THREADS]
-    uint32_t* const bS = base + 4 * PTS * THREADS + tid;                    // [3][PTS][THREADS]
+    state_t* const src_pl = reinterpret_cast<state_t*>(base) + tid;         // [PTS][THREADS]
+    state_t* const bS = src_pl + PTS * THREADS;                              // [3][PTS][THREADS]
+    float* const bD = reinterpret_cast<float*>(src_pl - tid + 4 * PTS * THREADS) + tid;   // [3][PTS][THREADS]
 
     const int n = a.n, k = a.k;
     const int rx = blockIdx.x * TX + threadIdx.x;
@@ -85,10 +86,10 @@ jfa_pass_lattice(const LatArgs a) {
     }
     const uint32_t okz = ((2u << lz) - 2u);    // outputs exist for planes 0 .. lz-1
 
-    auto load_plane = [&](int sp, uint32_t (&s)[PTS]) {
+    auto load_plane = [&](int sp, state_t (&s)[PTS]) {
         const int gz = a.z0 + rz + sp * k;
         const bool z_ok = gz >= 0 && gz < n;
-        const uint32_t* __restrict__ p =
+        const state_t* __restrict__ p =
             a.contiguous ? a.src[1] + ((ptrdiff_t)rz + (ptrdiff_t)sp * k) * (ptrdiff_t)plane
                          : (sp < 0 ? a.src[0] : (sp == 0 ? a.src[1] : a.src[2])) + (size_t)rz * plane;
 #pragma unroll
@@ -96,15 +97,15 @@ jfa_pass_lattice(const LatArgs a) {
 #pragma unroll
             for (int i = 0; i < L; ++i) {
                 const int gy = ry + j * k, gx = rx + i * k;
-                s[j * L + i] = (z_ok && gy < n && gx < n) ? __ldg(p + (size_t)gy * n + gx) : 0u;
+                s[j * L + i] = (z_ok && gy < n && gx < n) ? __ldg(p + (size_t)gy * n + gx) : (state_t)0;
             }
     };
 
-    uint32_t nxt[PTS];
+    state_t nxt[PTS];
     load_plane(-1, nxt);
     // ring slot of output plane 0
 #pragma unroll
-    for (int b = 0; b < PTS; ++b) { bD[(0 * PTS + b) * THREADS] = INFINITY; bS[(0 * PTS + b) * THREADS] = 0u; }
+    for (int b = 0; b < PTS; ++b) { bD[(0 * PTS + b) * THREADS] = INFINITY; bS[(0 * PTS + b) * THREADS] = 0; }
 
 #pragma unroll 1
     for (int sp = -1; sp <= lz; ++sp) {
@@ -121,7 +122,7 @@ jfa_pass_lattice(const LatArgs a) {
         const int slot_c = (sp + 3) % 3, slot_n = (sp + 4) % 3, slot_p = (sp + 2) % 3;
         if (sp + 1 < lz && sp >= 0) {          // ring slot of output plane sp+1 (plane 0's was set up front)
 #pragma unroll
-            for (int b = 0; b < PTS; ++b) { bD[(slot_n * PTS + b) * THREADS] = INFINITY; bS[(slot_n * PTS + b) * THREADS] = 0u; }
+            for (int b = 0; b < PTS; ++b) { bD[(slot_n * PTS + b) * THREADS] = INFINITY; bS[(slot_n * PTS + b) * THREADS] = 0; }
         }
         const int gz_c = a.z0 + rz + sp * k;
         // ---- outputs of plane sp: their own seed comes before every source of this plane --------------------------
@@ -132,7 +133,7 @@ jfa_pass_lattice(const LatArgs a) {
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1u;
                 const int jj = b >> 2, ii = b & 3, t = jj * L + ii;
-                const uint32_t s = src_pl[t * THREADS];
+                const state_t s = src_pl[t * THREADS];
                 const float d = __fadd_rn(__fadd_rn(sqdiff(ld(jfa_x(s)), ld(rx + ii * k)),
                                                     sqdiff(ld(MAXN + jfa_y(s)), ld(MAXN + ry + jj * k))),
                                           sqdiff(ld(2 * MAXN + jfa_z(s)), qz));
@@ -156,7 +157,7 @@ jfa_pass_lattice(const LatArgs a) {
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1u;
                 const int jj = b >> 2, ii = b & 3, t = jj * L + ii;
-                const uint32_t s = src_pl[t * THREADS];
+                const state_t s = src_pl[t * THREADS];
                 const float sx = ld(jfa_x(s)), sy = ld(MAXN + jfa_y(s)), sz = ld(2 * MAXN + jfa_z(s));
                 float X[3], Y[3], Z[3];
                 bool xo[3], yo[3];
@@ -189,7 +190,7 @@ jfa_pass_lattice(const LatArgs a) {
         // ---- output plane sp-1 has seen all of its sources --------------------------------------------------------
         if (sp >= 1) {
             const int zl = rz + (sp - 1) * k;
-            uint32_t* __restrict__ out = a.dst + (size_t)zl * plane;
+            state_t* __restrict__ out = a.dst + (size_t)zl * plane;
 #pragma unroll
             for (int j = 0; j < L; ++j)
 #pragma unroll
@@ -203,7 +204,7 @@ jfa_pass_lattice(const LatArgs a) {
 
 template <int L, bool LUT_SMEM>
 int launch(const LatArgs& a, dim3 grid, cudaStream_t st) {
-    constexpr size_t SMEM = ((size_t)7 * L * L * THREADS + (LUT_SMEM ? 3 * MAXN : 0)) * sizeof(uint32_t);
+    constexpr size_t SMEM = (size_t)L * L * THREADS * (4 * sizeof(state_t) + 3 * sizeof(float)) + (LUT_SMEM ? 3 * MAXN : 0) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         VPB_CUDA(cudaFuncSetAttribute(jfa_pass_lattice<L, LUT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -218,7 +219,7 @@ int launch(const LatArgs& a, dim3 grid, cudaStream_t st) {
 
 // Returns 1 when the pass is not one this kernel takes (the caller then runs the flood kernels), VPB_OK when launched.
 // VPB_JFA_LATTICE=0 turns it off (A/B timing, parity tests of the flood kernels on the same passes).
-int jfa_pass_lattice_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst,
+int VPB_SFX(jfa_pass_lattice_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
                             const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, cudaStream_t st) {
     const uint32_t n = f.n, T = z1 - z0;
     const char* env = getenv("VPB_JFA_LATTICE");
@@ -230,7 +231,7 @@ int jfa_pass_lattice_launch(const uint32_t* below, const uint32_t* mid, const ui
     a.n = (int)n; a.z0 = (int)z0; a.T = (int)T; a.k = (int)k;
     const ptrdiff_t kp = (ptrdiff_t)k * n * n;
     a.contiguous = (above == mid + kp) && (below == mid - kp);
-    a.lut = jfa_lut_launch(f, st);
+    a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
     const uint32_t res = k < n ? k : n;
     const uint32_t res_z = a.contiguous ? (k < T ? k : T) : T;

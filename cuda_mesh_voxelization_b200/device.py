@@ -43,7 +43,9 @@ class DeviceMesh:
 
 
 class DevicePipeline:
-    """Single-GPU voxelize -> CSG fold -> JFA SDF with all buffers resident.  N <= 1024 (32-bit seed state)."""
+    """Single-GPU voxelize -> CSG fold -> JFA SDF with all buffers resident.  The seed state is 4 B/voxel up to
+    N = 1024 and 8 B/voxel up to 2048 (vpb_jfa_state_bytes tells); above 1024 the signed distance is written into the
+    state buffer the final pass leaves free, so that 2048^3 (2 x 64 GiB of state) fits one 180 GB GPU."""
 
     def __init__(self, n: int, voxel_size, origin, device="cuda:0", want_seeds=False, max_tris=0):
         self.lib = capi.load()
@@ -57,9 +59,13 @@ class DevicePipeline:
         i32 = dict(dtype=torch.int32, device=self.device)
         self.grid_a = torch.empty(nw, **i32)
         self.grid_b = torch.empty(nw, **i32)
-        self.state_a = torch.empty(vox, **i32)
-        self.state_b = torch.empty(vox, **i32)
-        self.sdf = torch.empty(vox, dtype=torch.float32, device=self.device)
+        self.state_bytes = int(self.lib.vpb_jfa_state_bytes(self.n, 0, self.n))
+        self.state_a = torch.empty(self.state_bytes // 4, **i32)
+        self.state_b = torch.empty(self.state_bytes // 4, **i32)
+        if want_seeds and self.n > 1024:
+            raise ValueError("the public 10-bit seed encoding needs N <= 1024")
+        self.alias_sdf = self.n > 1024
+        self.sdf = None if self.alias_sdf else torch.empty(vox, dtype=torch.float32, device=self.device)
         self.seeds = torch.empty(vox, **i32) if want_seeds else None
         self.scratch = None
         self._reserve_scratch(max_tris)
@@ -86,11 +92,15 @@ class DevicePipeline:
         n, st = self.n, _stream()
         capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_a), n, 0, n, _ptr(self.state_a), st))
         src, dst = self.state_a, self.state_b
+        if self.alias_sdf:      # the final pass (or finalize) never writes its state destination
+            passes = max(n.bit_length() - 1, 0)
+            free = self.state_b if passes % 2 == 1 or passes == 0 else self.state_a
+            self.sdf = free.view(torch.float32)[:n ** 3]
         if n // 2 == 0:
             capi.check(self.lib.vpb_jfa_finalize_dev(_ptr(src), n, 0, n, self.vs, self._o(), _ptr(self.grid_a),
                                                      _ptr(self.sdf), _ptr(self.seeds), st))
             return
-        plane_bytes = n * n * 4
+        plane_bytes = self.state_bytes // n
         k = n // 2
         while k >= 1:
             last = k == 1

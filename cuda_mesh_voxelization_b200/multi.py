@@ -107,8 +107,10 @@ class SlabPipeline:
         from . import capi
         self.torch, self.capi = torch, capi
         self.lib = capi.load()
-        if n % 32 or n > 1024:
-            raise ValueError("slab pipeline needs N % 32 == 0 and N <= 1024")
+        if n % 32 or n > 2048:
+            raise ValueError("slab pipeline needs N % 32 == 0 and N <= 2048")
+        if want_seeds and n > 1024:
+            raise ValueError("the public 10-bit seed encoding needs N <= 1024")
         self.plan = SlabPlan(n, rank, world)
         self.n, self.vs = int(n), float(voxel_size)
         self.origin = np.ascontiguousarray(origin, np.float32)
@@ -116,18 +118,23 @@ class SlabPipeline:
         self.comm = comm
         capi.init(self.device.index or 0)
         p = self.plan
-        self.plane = n * n
-        self.slab_voxels = self.plane * p.T
+        self.slab_voxels = n * n * p.T
+        # state element: 4 B up to N = 1024, 8 B above (or with VPB_JFA_STATE64=1); buffers are int32 tensors, so a
+        # "plane" below is n*n*w32 int32 elements
+        self.esz = int(self.lib.vpb_jfa_state_bytes(n, p.z0, p.z1)) // self.slab_voxels
+        self.w32 = self.esz // 4
+        self.plane = n * n * self.w32
+        self.bit_plane = n * n
         i32 = dict(dtype=torch.int32, device=self.device)
         self.grid_full = torch.zeros(capi.n_words(n), **i32)
-        wslab = self.plane * p.T // 32
+        wslab = self.bit_plane * p.T // 32
         self.grid_slab = self.grid_full[rank * wslab:(rank + 1) * wslab]     # a view: CSG result lands in place
         self.grid_b = torch.empty(wslab, **i32)
         # peer mode: state in symmetric memory, read by the neighbours' kernels over NVLink (needs N % 64 == 0 for the
         # key-based flood kernel); opt-in, see the module docstring for the measurement
         import os
         if peer is None:
-            peer = os.environ.get("VPB_PEER") == "1" and comm is None and world > 1 and n % 64 == 0
+            peer = os.environ.get("VPB_PEER") == "1" and comm is None and world > 1 and n % 64 == 0 and self.esz == 4
         self.peer = bool(peer)
         self.symm = None
         if self.peer:
@@ -143,7 +150,7 @@ class SlabPipeline:
         if not self.peer:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
             self.ext = [torch.zeros((p.H + p.T + p.H) * self.plane, **i32) for _ in range(2)]
-            self.far = [torch.empty(self.slab_voxels, **i32) for _ in range(2)] if world > 1 else [None, None]
+            self.far = [torch.empty(self.slab_voxels * self.w32, **i32) for _ in range(2)] if world > 1 else [None, None]
         self.sdf = torch.empty(self.slab_voxels, dtype=torch.float32, device=self.device)
         self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
         self.scratch = None
@@ -265,7 +272,7 @@ class SlabPipeline:
                 self.pass_events.append((k, e0, e1))
             return
         mid = self.center(cur).data_ptr()
-        kb = k * self.plane * 4
+        kb = k * self.plane * 4          # self.plane counts int32 elements
         if k < p.T or p.world == 1:
             below, above = mid - kb, mid + kb            # contiguous extended buffer
         else:
