@@ -113,7 +113,7 @@ def ncu_traffic():
 
 # ------------------------------------------------------------------------------------------ reference arm
 
-def cpu_pipeline(lib, kind, meshes, n, origin_vs=None):
+def cpu_pipeline(lib, kind, meshes, n, origin_vs=None, op=1):
     """One pass of the reference CPU path (-t 3 flavour: sequential voxelization — the only CPU voxelizer the CLI
     ever calls, apps/cli/main.cpp:99-103 — then OpenMP CSG and JFA with every host thread)."""
     if origin_vs is None:
@@ -123,10 +123,10 @@ def cpu_pipeline(lib, kind, meshes, n, origin_vs=None):
     t0 = time.perf_counter()
     grids = [lib.voxelize(*m, n, vs, origin) for m in meshes]
     if kind == "reference":
-        acc = lib.csg(grids[0], grids[1], n, 1, openmp=True)
+        acc = lib.csg(grids[0], grids[1], n, op, openmp=True)
         lib.jfa(acc, n, vs, origin, openmp=True)
     else:
-        acc = lib.csg(grids[0], grids[1], n, 1)
+        acc = lib.csg(grids[0], grids[1], n, op)
         lib.jfa(acc, n, vs, origin)
     return time.perf_counter() - t0
 
@@ -148,8 +148,8 @@ def run_reference(args):
     n_s = args.ref_n
     meshes, _, _ = load_workload(n_s, args.faces)
     for _ in range(args.warmup):
-        cpu_pipeline(lib, kind, meshes, n_s)
-    t = [cpu_pipeline(lib, kind, meshes, n_s) for _ in range(args.steps)]
+        cpu_pipeline(lib, kind, meshes, n_s, op=OPS[args.op][0])
+    t = [cpu_pipeline(lib, kind, meshes, n_s, op=OPS[args.op][0]) for _ in range(args.steps)]
     total = sum(t)
     value = n_s ** 3 * args.steps / total / 1e9
     sample = (f"{n_s}^3 grid per step (the workload's meshes and stages at 1/{(args.n // n_s) ** 3} of its voxels): "
@@ -166,9 +166,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+OPS = {"union": (1, "∪"), "intersection": (2, "∩"), "difference": (3, "−")}
+
+
 def workload_name(args):
-    return (f"bunny subdivided to {args.faces} faces ∪ bimba (46220 faces), solid voxelization + CSG union + JFA SDF "
-            f"at {args.n}^3")
+    return (f"bunny subdivided to {args.faces} faces {OPS[args.op][1]} bimba (46220 faces), solid voxelization + CSG "
+            f"{args.op} + JFA SDF at {args.n}^3")
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -208,8 +211,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    op = OPS[args.op][0]
     for _ in range(args.warmup):
-        pipe.run(dmeshes, op=capi.OP_UNION, sdf=True)
+        pipe.run(dmeshes, op=op, sdf=True)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -222,7 +226,7 @@ def run_ours(args):
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        pipe.run(dmeshes, op=capi.OP_UNION, sdf=True, record_passes=True)
+        pipe.run(dmeshes, op=op, sdf=True, record_passes=True)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -254,13 +258,14 @@ def run_ours(args):
         dist.all_gather(allt, t)
         stage_ranks = {k_: [round(float(a[i]), 2) for a in allt] for i, k_ in enumerate(keys)}
     peak, peak_src = hbm_peak()
-    alg_bytes = 8.0 * slab_voxels  # 4 B state read + 4 B state (or sdf) write per voxel per pass
+    esz = 8 if n > 1024 else 4     # seed state width (vpb_jfa_state_bytes): 4 B up to 1024^3, 8 B above
+    alg_bytes = 2.0 * esz * slab_voxels  # state read + state (or sdf) write per voxel per pass (2*s B/voxel)
     achieved = alg_bytes / (mean_pass_ms * 1e-3) / 1e9 if mean_pass_ms else None
     traffic = ncu_traffic()
 
     # ---- end to end through the reference-facing C-ABI call, host buffers, copies inside the timed region
     e2e = None
-    if world == 1:
+    if world == 1 and n <= 1024:   # above 1024^3 the host-side SDF alone is 32 GiB of pinned memory: device-resident only
         pv = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v, _ in meshes]
         pt = [torch.from_numpy(np.ascontiguousarray(t).view(np.int32)).pin_memory() for _, t in meshes]
         host_meshes = [(a.numpy(), b.numpy().view(np.uint32)) for a, b in zip(pv, pt)]
@@ -268,7 +273,7 @@ def run_ours(args):
         words_host = torch.empty(capi.n_words(n), dtype=torch.int32).pin_memory()
         del pipe
         torch.cuda.empty_cache()
-        kw = dict(op=capi.OP_UNION, sdf_out=sdf_host.numpy(), words_out=words_host.numpy().view(np.uint32))
+        kw = dict(op=op, sdf_out=sdf_host.numpy(), words_out=words_host.numpy().view(np.uint32))
         for _ in range(max(1, min(args.warmup, 2))):
             capi.pipeline_host(host_meshes, n, vs, origin, **kw)
         t0 = time.perf_counter()
@@ -294,7 +299,7 @@ def run_ours(args):
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         n_s = args.ref_n
         ms_, _, _ = load_workload(n_s, args.faces)
-        dt = cpu_pipeline(lib, kind, ms_, n_s)
+        dt = cpu_pipeline(lib, kind, ms_, n_s, op=OPS[args.op][0])
         cpu = {"value": n_s ** 3 / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"one step at {n_s}^3 (same meshes and stages, 1/{(n // n_s) ** 3} of the voxels): sequential "
                          f"voxelization + OpenMP CSG + OpenMP JFA, {dt:.2f} s"}
@@ -304,8 +309,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": "union",
-                   "l2": "per-step working set (2 x 4.3 GB seed state + 4.3 GB sdf) >> 126 MB L2, no flush needed",
+        "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": args.op,
+                   "l2": f"per-step working set (2 x {esz * n ** 3 / 1e9:.1f} GB seed state + {4 * n ** 3 / 1e9:.1f} GB sdf) "
+                         ">> 126 MB L2, no flush needed",
                    "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass",
                    **({"stage_ms_rank0": stage_ms} if stage_ms else {}),
                    **({"stage_ms_by_rank": stage_ranks} if stage_ranks else {})},
@@ -326,8 +332,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=1024, help="grid side (use --grid under torchrun: its parser rejects --n)")
     ap.add_argument("--faces", type=int, default=1348128)
+    ap.add_argument("--op", default="union", choices=sorted(OPS), help="CSG operator folding bimba into the bunny")
     ap.add_argument("--ref-n", type=int, default=128, help="grid side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
