@@ -65,6 +65,7 @@ struct F4Args {
     uint32_t key_k0;          // -(key_base * 16) mod 2^32
     float bigz;               // z coordinate staged for "no seed"
     float neg_zero;           // -0.0f, deliberately a RUNTIME value: see sq2() in jfa_tiled.cu
+    float ox, oy, oz, vs4;    // frame origin and voxelSize / 4 (ARITH staging)
 };
 
 template <int SS, int TR>
@@ -80,6 +81,11 @@ struct Cfg {
     static constexpr int NP = (ITEMS + THREADS - 1) / THREADS;
     static constexpr int NBUF = SS >= 64 ? 1 : 2;     // float planes double-buffered unless the window is 192 wide
     static constexpr size_t SMEM = ((size_t)3 * MAXN + (size_t)NBUF * 3 * PW) * 4 + (size_t)4 * PW * sizeof(state_t);
+    // Staging turns a packed seed into world coordinates.  For k <= 8 neighbouring voxels hold neighbouring seeds and the
+    // three table reads are conflict-free; in the early passes (k >= 16) the seeds of a row are scattered and the reads
+    // serialise on shared-memory banks (ncu: 1.1e9 conflict wavefronts of 2.6e9 at k = 64, LSU 74 % busy).  There the
+    // coordinate is rebuilt arithmetically instead: origin + float(i) * voxelSize, the tables' own expression.
+    static constexpr bool ARITH = SS >= 16;
 };
 
 __device__ __forceinline__ float2 sq2(float2 x, float2 nz) { return __ffma2_rn(x, x, nz); }
@@ -198,6 +204,20 @@ struct Flood4 {
             const float zz = *reinterpret_cast<const float*>(l + 8 * MAXN + jfa_offz(s));
             z = s ? zz : a.bigz;
         };
+        // float(4*i) without I2F: 0x4B000000 | m is 2^23 + m exactly; (4 i) * (vs / 4) is the same real number as i * vs, so
+        // it rounds to the same float (vs / 4 is exact; frame_supports_keys keeps vs far from the denormal range).  The
+        // product is written fma(a, b, -0) with a run-time -0 so that ptxas cannot contract it with the add (see sq2()).
+        auto conv_arith = [&](state_t s0, state_t s1, float2& x, float2& y, float2& z) {
+            const float2 m = make_float2(-8388608.0f, -8388608.0f), v4 = make_float2(a.vs4, a.vs4);
+            const float2 ix = __fadd2_rn(make_float2(__uint_as_float(jfa_offx(s0) | 0x4B000000u), __uint_as_float(jfa_offx(s1) | 0x4B000000u)), m);
+            const float2 iy = __fadd2_rn(make_float2(__uint_as_float(jfa_offy(s0) | 0x4B000000u), __uint_as_float(jfa_offy(s1) | 0x4B000000u)), m);
+            const float2 iz = __fadd2_rn(make_float2(__uint_as_float(jfa_offz(s0) | 0x4B000000u), __uint_as_float(jfa_offz(s1) | 0x4B000000u)), m);
+            x = __fadd2_rn(make_float2(a.ox, a.ox), __ffma2_rn(ix, v4, nz));
+            y = __fadd2_rn(make_float2(a.oy, a.oy), __ffma2_rn(iy, v4, nz));
+            z = __fadd2_rn(make_float2(a.oz, a.oz), __ffma2_rn(iz, v4, nz));
+            z.x = s0 ? z.x : a.bigz;
+            z.y = s1 ? z.y : a.bigz;
+        };
         auto stage = [&](int p) {
             float* f = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW;
             state_t* ps = ring + ((p + 1) & 3) * C::PW;
@@ -207,8 +227,12 @@ struct Flood4 {
                 const int e = ((int)threadIdx.x + C::THREADS * v) * C::G;
                 if (C::ALIGNED) {
                     float2 x, y, z;
-                    conv(stq[v][0], x.x, y.x, z.x);
-                    conv(stq[v][C::G - 1], x.y, y.y, z.y);
+                    if (C::ARITH) {
+                        conv_arith(stq[v][0], stq[v][C::G - 1], x, y, z);
+                    } else {
+                        conv(stq[v][0], x.x, y.x, z.x);
+                        conv(stq[v][C::G - 1], x.y, y.y, z.y);
+                    }
                     *reinterpret_cast<float2*>(f + e) = x;
                     *reinterpret_cast<float2*>(f + C::PW + e) = y;
                     *reinterpret_cast<float2*>(f + 2 * C::PW + e) = z;
@@ -429,6 +453,7 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
     a.key_k0 = 0u - a.key_base * 16u;
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
     a.neg_zero = -0.0f;
+    a.ox = f.ox; a.oy = f.oy; a.oz = f.oz; a.vs4 = f.vs * 0.25f;
     a.glut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.glut) return VPB_ERR_CUDA;
     const ptrdiff_t kp = (ptrdiff_t)k * n * n;
