@@ -220,6 +220,7 @@ def run_ours(args):
         sampler.start()
     launches0 = capi.kernel_launches()
     pipe.pass_events.clear()
+    pipe.early_events.clear()
     if hasattr(pipe, "stage_events"):
         pipe.stage_events = []
     e0 = torch.cuda.Event(enable_timing=True)
@@ -243,6 +244,7 @@ def run_ours(args):
     slab_voxels = pipe.slab_voxels if world > 1 else n ** 3
     pass_avg = {k: float(np.mean(v)) for k, v in pass_ms.items()}
     mean_pass_ms = float(np.mean([np.mean(v) for v in pass_ms.values()])) if pass_ms else None
+    early_ms = float(np.mean([a.elapsed_time(b) for a, b in pipe.early_events])) if pipe.early_events else None
     stage_ms = None
     if getattr(pipe, "stage_events", None):
         stage_ms = {}
@@ -315,10 +317,11 @@ def run_ours(args):
                    "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass",
                    **({"stage_ms_rank0": stage_ms} if stage_ms else {}),
                    **({"stage_ms_by_rank": stage_ranks} if stage_ranks else {})},
-        "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the log2(N) passes of a step)",
+        "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the flood passes of a step: k = N/16 .. 1 when the "
+                                                "fused seed + first-three-passes kernel ran, else all log2(N))",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
-                     "ms_per_launch": mean_pass_ms, "ms_per_pass_by_k": {str(k): v for k, v in sorted(pass_avg.items(), reverse=True)}},
+                     "ms_per_launch": mean_pass_ms, "ms_early_seed_plus_3_passes": early_ms, "ms_per_pass_by_k": {str(k): v for k, v in sorted(pass_avg.items(), reverse=True)}},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -335,9 +338,13 @@ def main():
     ap.add_argument("--n", "--grid", dest="n", type=int, default=1024, help="grid side (use --grid under torchrun: its parser rejects --n)")
     ap.add_argument("--faces", type=int, default=1348128)
     ap.add_argument("--op", default="union", choices=sorted(OPS), help="CSG operator folding bimba into the bunny")
-    ap.add_argument("--ref-n", type=int, default=128, help="grid side of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=0,
+                    help="grid side of the bounded CPU sample (default: 512 for the cpu_baseline of our arm = ~20-30 s of CPU "
+                         "work once, 256 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if not args.ref_n:
+        args.ref_n = 256 if args.impl == "reference" else 512
     if args.impl == "reference":
         run_reference(args)
     else:

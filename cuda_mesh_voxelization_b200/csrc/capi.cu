@@ -78,6 +78,11 @@ size_t state_size(uint32_t n) { return jfa_state64(n) ? 8 : 4; }
 int seed_any(const uint32_t* words, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st) {
     return jfa_state64(n) ? jfa_seed_launch_s64(words, n, z0, z1, state, st) : jfa_seed_launch(words, n, z0, z1, state, st);
 }
+int early_any(const uint32_t* words, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch, uint32_t* state,
+              cudaStream_t st) {
+    return jfa_state64(f.n) ? jfa_early_launch_s64(words, f, z0, z1, shell_scratch, state, st)
+                            : jfa_early_launch(words, f, z0, z1, shell_scratch, state, st);
+}
 int pass_any(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f, uint32_t z0,
              uint32_t z1, uint32_t k, const uint32_t* words, float* sdf, uint32_t* seeds, cudaStream_t st) {
     return jfa_state64(f.n) ? jfa_pass_launch_s64(below, mid, above, dst, f, z0, z1, k, words, sdf, seeds, st)
@@ -95,7 +100,15 @@ int finalize_any(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1
 int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st,
             float** sdf_at = nullptr) {
     const uint32_t n = f.n;
-    VPB_TRY(seed_any(words, n, 0, n, sa, st));
+    // seed extraction + the passes k = N/2, N/4, N/8 fused (jfa_early.cu; the shell bits go through the free buffer sb),
+    // or, for shapes it does not take, seed extraction and every pass on its own
+    uint32_t k_first = n / 2;
+    {
+        const int rc = early_any(words, f, 0, n, sb, sa, st);
+        if (rc < 0) return rc;
+        if (rc == 0) k_first = n / 16;
+        else VPB_TRY(seed_any(words, n, 0, n, sa, st));
+    }
     const uint64_t plane_bytes = (uint64_t)n * n * state_size(n);
     char* in = reinterpret_cast<char*>(sa);
     char* out = reinterpret_cast<char*>(sb);
@@ -104,7 +117,7 @@ int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, f
         if (sdf_at) *sdf_at = target;
         return finalize_any(sa, f, 0, n, words, target, seeds, st);
     }
-    for (uint32_t k = n / 2; k >= 1; k /= 2) {
+    for (uint32_t k = k_first; k >= 1; k /= 2) {
         const bool last = (k == 1);
         float* target = sdf ? sdf : reinterpret_cast<float*>(out);
         if (last && sdf_at) *sdf_at = target;
@@ -224,6 +237,21 @@ size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1) {
 int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, void* stream) {
     VPB_TRY(require_ready());
     return seed_any(words_full, n, z0, z1, state, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_jfa_early_supported(uint32_t n, float vs, const float origin[3]) {
+    if (!origin || n == 0 || n > kMaxJfaN) return 0;
+    const Frame f = make_frame(n, vs, origin);
+    return jfa_state64(n) ? jfa_early_supported_s64(f) : jfa_early_supported(f);
+}
+
+int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, float vs, const float origin[3],
+                      uint32_t* shell_scratch, uint32_t* state, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && words_full && shell_scratch && state, "jfa_early: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && z0 < z1 && z1 <= n, "jfa_early: bad n=%u slab [%u,%u)", n, z0, z1);
+    return early_any(words_full, make_frame(n, vs, origin), z0, z1, shell_scratch, state,
+                     stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
 int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, uint32_t n,

@@ -125,6 +125,13 @@ int jfa_pass_flood_peer_launch(const uint32_t* const* slabs, uint32_t world, uin
                                float* sdf, uint32_t* seeds, cudaStream_t st);
 int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
                         float* sdf, uint32_t* seeds, cudaStream_t st);
+// seed extraction + the passes k = N/2, N/4, N/8 in one kernel (jfa_early.cu); 1 = shape/frame not taken, caller runs them one by one
+int jfa_early_launch(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
+                     uint32_t* state, cudaStream_t st);
+int jfa_early_supported(const Frame& f);
+int jfa_early_supported_s64(const Frame& f);
+int jfa_early_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
+                         uint32_t* state, cudaStream_t st);
 // the same three with the 64-bit state (N <= 2048); state pointers are uint64_t* behind the uint32_t* of the C ABI
 int jfa_seed_launch_s64(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_pass_launch_s64(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,

@@ -70,6 +70,7 @@ class DevicePipeline:
         self.scratch = None
         self._reserve_scratch(max_tris)
         self.pass_events = []  # [(k, start_event, end_event)] when record_passes=True
+        self.early_events = []  # [(start_event, end_event)] of the fused seed + first-three-passes kernel
 
     def _reserve_scratch(self, n_tris):
         need = int(self.lib.vpb_voxelize_scratch_bytes(self.n, n_tris, 0, self.n))
@@ -90,8 +91,25 @@ class DevicePipeline:
 
     def jfa(self, record_passes=False):
         n, st = self.n, _stream()
-        capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_a), n, 0, n, _ptr(self.state_a), st))
-        src, dst = self.state_a, self.state_b
+        # seed extraction + the passes k = N/2, N/4, N/8 in one kernel where the library takes the grid (the result lands
+        # in state_b, where three ping-pong passes would have left it; state_a is the scratch of the shell bits)
+        if record_passes:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = self.lib.vpb_jfa_early_dev(_ptr(self.grid_a), n, 0, n, self.vs, self._o(), _ptr(self.state_a),
+                                        _ptr(self.state_b), st) if n >= 16 else 1
+        if rc < 0:
+            capi.check(rc)
+        if record_passes and rc == 0:
+            e1.record()
+            self.early_events.append((e0, e1))
+        early = rc == 0
+        if early:
+            src, dst = self.state_b, self.state_a
+        else:
+            capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_a), n, 0, n, _ptr(self.state_a), st))
+            src, dst = self.state_a, self.state_b
         if self.alias_sdf:      # the final pass (or finalize) never writes its state destination
             passes = max(n.bit_length() - 1, 0)
             free = self.state_b if passes % 2 == 1 or passes == 0 else self.state_a
@@ -101,7 +119,7 @@ class DevicePipeline:
                                                      _ptr(self.sdf), _ptr(self.seeds), st))
             return
         plane_bytes = self.state_bytes // n
-        k = n // 2
+        k = n // 16 if early else n // 2
         while k >= 1:
             last = k == 1
             base = src.data_ptr()

@@ -5,7 +5,10 @@ Partition.  Rank r owns the planes z in [r*T, (r+1)*T), T = N / wo
                          carry, no communication.  Every rank rasterises the full mesh clipped to its slab.
   * occupancy          : all-gathered once (N^3/8 bytes in total) — seed extraction needs one plane either side
                          and the final pass needs the sign; the bit grid is tiny next to the seed state.
-  * JFA passes         : one halo exchange per pass.  A voxel at z needs planes z-k and z+k:
+  * first three passes : k = N/2, N/4, N/8 couple only voxels that are equal mod N/8, so every rank runs them for its own
+                         planes from the (all-gathered) occupancy bits in ONE kernel with no exchange at all
+                         (vpb_jfa_early_dev; each rank walks every 8x8x8 lattice and keeps the planes of its slab).
+  * JFA passes         : one halo exchange per remaining pass.  A voxel at z needs planes z-k and z+k:
         k <  T : k boundary planes from each adjacent rank, received straight into the halo region of an
                  extended buffer [T/2 | T | T/2 planes] so the pass kernel sees one contiguous z range;
         k >= T : the whole slab of rank r -/+ k/T (NVSwitch: any peer at full bandwidth), received into two
@@ -121,6 +124,10 @@ class SlabPipeline:
         self.slab_voxels = n * n * p.T
         # state element: 4 B up to N = 1024, 8 B above (or with VPB_JFA_STATE64=1); buffers are int32 tensors, so a
         # "plane" below is n*n*w32 int32 elements
+        # seed extraction + the passes k = N/2, N/4, N/8 fused and exchange-free (vpb_jfa_early_dev) where the library takes
+        # the grid; the remaining passes are self.steps
+        self.use_early = bool(self.lib.vpb_jfa_early_supported(n, self.vs, self._o())) and n // 16 >= 1
+        self.steps = [k for k in p.steps() if not self.use_early or k < n // 8]
         self.esz = int(self.lib.vpb_jfa_state_bytes(n, p.z0, p.z1)) // self.slab_voxels
         self.w32 = self.esz // 4
         self.plane = n * n * self.w32
@@ -151,7 +158,7 @@ class SlabPipeline:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
             self.ext = [torch.zeros((p.H + p.T + p.H) * self.plane, **i32) for _ in range(2)]
             # far-slab receive buffers (k >= T passes), only the sides this rank ever receives on
-            roles = {t.role for k in p.steps() if k >= p.T for t in p.recvs(k)} if world > 1 else set()
+            roles = {t.role for k in self.steps if k >= p.T for t in p.recvs(k)} if world > 1 else set()
             self.far = [torch.empty(self.slab_voxels * self.w32, **i32) if r in roles else None for r in ("below", "above")]
         # the final pass writes the signed distance INSTEAD of its state destination; above 1024^3 it goes into that
         # free state buffer (saves 4 B/voxel of HBM: 2048^3 on 2 GPUs would not fit otherwise)
@@ -164,6 +171,7 @@ class SlabPipeline:
         self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
         self.scratch = None
         self.pass_events = []
+        self.early_events = []
 
     def _setup_peer(self):
         """Two ping-pong state buffers in symmetric memory + the table of every rank's mapped address."""
@@ -234,6 +242,17 @@ class SlabPipeline:
         p = self.plan
         self.capi.check(self.lib.vpb_jfa_seed_dev(_ptr(self.grid_full), self.n, p.z0, p.z1, _ptr(self.center(0)),
                                                   self._stream()))
+
+    def early(self):
+        """Seed extraction + the first three passes for this slab; the result lands in buffer 1 (where three ping-pong
+        passes starting from buffer 0 would have left it), buffer 0 is the scratch of the seed-shell bits."""
+        p = self.plan
+        scratch = self.center(0)
+        assert scratch.numel() * 4 >= self.capi.n_words(self.n) * 4, "state slab smaller than the bit grid"
+        rc = self.lib.vpb_jfa_early_dev(_ptr(self.grid_full), self.n, p.z0, p.z1, self.vs, self._o(), _ptr(scratch),
+                                        _ptr(self.center(1)), self._stream())
+        if rc != 0:
+            self.capi.check(rc if rc < 0 else -1)
 
     def exchange(self, k, cur):
         """Halo exchange for step k on the current state buffer `cur` (0/1)."""
@@ -319,11 +338,23 @@ class SlabPipeline:
         self._mark(record_passes, "allgather_bits")
         if not sdf:
             return
-        self.seed()
+        if self.use_early:
+            if self.peer:
+                self.peer_barrier(0)          # buffer 0 is about to become scratch: nobody may still be reading it
+            if record_passes:
+                e0 = self.torch.cuda.Event(enable_timing=True)
+                e1 = self.torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.early()
+            if record_passes:
+                e1.record()
+                self.early_events.append((e0, e1))
+            cur = 1
+        else:
+            self.seed()
+            cur = 0
         self._mark(record_passes, "seed")
-        cur = 0
-        steps = self.plan.steps()
-        for k in steps:
+        for k in self.steps:
             self.exchange(k, cur)
             self._mark(record_passes, "exchange")
             self.flood(k, cur, last=(k == 1), record=record_passes)
@@ -358,9 +389,9 @@ class LocalComm:
                 w = q.grid_slab.numel()
                 p.grid_full[q.plan.rank * w:(q.plan.rank + 1) * w].copy_(q.grid_slab)
         for p in R:
-            p.seed()
-        cur = 0
-        for k in R[0].plan.steps():
+            p.early() if p.use_early else p.seed()
+        cur = 1 if R[0].use_early else 0
+        for k in R[0].steps:
             for p in R:                                   # every receive pulls from the sender's current centre
                 for t in p.plan.recvs(k):
                     src = R[t.peer].center(cur)[t.src_lo * p.plane:(t.src_lo + t.count) * p.plane]

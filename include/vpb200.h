@@ -105,6 +105,16 @@ VPB_API size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1);
 /* Seed extraction for slab [z0,z1) from the FULL occupancy grid (needs planes z0-1 and z1). */
 VPB_API int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state_slab,
                              void* stream);
+/* Seed extraction AND the first three flood passes (k = N/2, N/4, N/8) for slab [z0,z1) in one kernel
+ * (vplib/src/jfa/sequential.cpp:24-63 + the first three iterations of the loop at :72): these passes only couple voxels
+ * that are equal mod N/8, so they run per 8x8x8 lattice in shared memory, straight from the seed-shell bits; on several
+ * GPUs they need no exchange although k >= slab thickness.  shell_scratch: ceil(N^3/32) words of scratch (receives the
+ * seed shell of the full grid).  Returns 0 when done -- continue with vpb_jfa_pass_dev at k = N/16 --, 1 when the shape
+ * or frame is not taken (N % 64 != 0, degenerate frame, VPB_JFA_EARLY=0): then run vpb_jfa_seed_dev and every pass. */
+/* 1 if vpb_jfa_early_dev takes this grid (what a multi-GPU driver needs to know before it sizes its exchange buffers) */
+VPB_API int vpb_jfa_early_supported(uint32_t n, float voxel_size, const float origin[3]);
+VPB_API int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
+                              const float origin[3], uint32_t* shell_scratch, uint32_t* state_slab, void* stream);
 /* One flood pass with step k over slab [z0,z1).  src_below/src_mid/src_above point at the state of plane
  * (z0 - k), z0 and (z0 + k) respectively, each followed by the next (z1-z0-1) planes; planes outside the grid
  * are never dereferenced, so the pointer may be anything there.  On one GPU: mid = in, below = in - k*N*N,

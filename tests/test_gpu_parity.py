@@ -227,6 +227,67 @@ def test_lattice_first_passes_equal_flood_passes_512(meshes, oracle, vpb, monkey
     assert np.array_equal(seeds_l, seeds_f)
 
 
+@pytest.mark.parametrize("mesh,n", [("torus", 64), ("bunny", 128), ("bimba", 192), ("d20", 256)])
+def test_fused_early_passes_equal_single_passes_and_oracle(mesh, n, meshes, oracle, vpb, monkeypatch):
+    """jfa_early.cu runs seed extraction + the passes k = N/2, N/4, N/8 in one kernel (shared-memory lattices, push form,
+    atomicMin keys); VPB_JFA_EARLY=0 runs them one by one, VPB_JFA_EARLY=16 uses the 16-lattice tile.  Same SDF bits and
+    the same nearest seeds (tie-breaking), and both equal the oracle."""
+    v, t = meshes[mesh]
+    origin, vs = oracle.frame(v, n)
+    words = oracle.voxelize(v, t, n, vs, origin)
+    import ctypes
+    o32 = np.ascontiguousarray(origin, np.float32)
+    assert vpb.load().vpb_jfa_early_supported(n, float(vs), o32.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == (
+        1 if n % 64 == 0 else 0)
+    sdf_e, seeds_e = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_EARLY", "16")
+    sdf_w, seeds_w = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_EARLY", "0")
+    sdf_s, seeds_s = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_EARLY")
+    assert np.array_equal(sdf_e.view(np.uint32), sdf_s.view(np.uint32))
+    assert np.array_equal(seeds_e, seeds_s)
+    assert np.array_equal(sdf_w.view(np.uint32), sdf_s.view(np.uint32))
+    assert np.array_equal(seeds_w, seeds_s)
+    if n <= 192:
+        osdf, oseeds = oracle.jfa(words, n, vs, origin, want_seeds=True)
+        assert np.array_equal(sdf_e.view(np.uint32), osdf.view(np.uint32))
+        assert np.array_equal(seeds_e, _public_seeds(oseeds, n))
+
+
+def test_fused_early_passes_512_and_wide_state(meshes, oracle, vpb, monkeypatch):
+    """Config 3 (1 348 128 faces, 512^3): fused early kernel == pass-by-pass, for the 32-bit and the 64-bit state."""
+    from cuda_mesh_voxelization_b200 import meshgen
+    v, t = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
+    n = 512
+    origin, vs = oracle.frame(v, n)
+    words = vpb.voxelize_host(v, t, n, vs, origin)
+    sdf_e, seeds_e = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.setenv("VPB_JFA_EARLY", "0")
+    sdf_s, seeds_s = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_EARLY")
+    assert np.array_equal(sdf_e.view(np.uint32), sdf_s.view(np.uint32))
+    assert np.array_equal(seeds_e, seeds_s)
+    monkeypatch.setenv("VPB_JFA_STATE64", "1")
+    sdf_w, seeds_w = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_STATE64")
+    assert np.array_equal(sdf_w.view(np.uint32), sdf_s.view(np.uint32))
+    assert np.array_equal(seeds_w, seeds_s)
+
+
+def test_fused_early_passes_dense_random_grid(oracle, vpb, monkeypatch):
+    """The worst case for the push form: half of the voxels are seeds, every pass is full of exact ties."""
+    n = 64
+    rng = np.random.default_rng(11)
+    words = rng.integers(0, 2 ** 32, n ** 3 // 32, dtype=np.uint32)
+    for origin, vs in [(np.array([-1.0, -1.0, -1.0], np.float32), np.float32(2.0 / n)),
+                       (np.array([0.3, -7.7, 2.1], np.float32), np.float32(0.0137))]:
+        sdf_e, seeds_e = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+        osdf, oseeds = oracle.jfa(words, n, vs, origin, want_seeds=True)
+        assert np.array_equal(sdf_e.view(np.uint32), osdf.view(np.uint32))
+        assert np.array_equal(seeds_e, _public_seeds(oseeds, n))
+
+
 def test_tiled_pass_on_random_dense_ties(oracle, vpb):
     """Random occupancy at N=64/128: every pass is full of exact distance ties; scan order must decide identically."""
     for n, seed in [(64, 1), (128, 2)]:
