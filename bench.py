@@ -100,10 +100,11 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per JFA-pass launch from the committed ncu capture summary, if any (profiles/*.json)."""
+def ncu_traffic(n, world):
+    """dram bytes per JFA-pass launch from the committed ncu --set full capture (profiles/jfa_pass_traffic.json); the
+    capture is of the 1024^3 single-GPU workload, so it is only quoted for that one."""
     p = os.path.join(ROOT, "profiles", "jfa_pass_traffic.json")
-    if os.path.exists(p):
+    if n == 1024 and world == 1 and os.path.exists(p):
         try:
             return float(json.load(open(p))["dram_bytes_per_launch"])
         except Exception:
@@ -263,7 +264,7 @@ def run_ours(args):
     esz = 8 if n > 1024 else 4     # seed state width (vpb_jfa_state_bytes): 4 B up to 1024^3, 8 B above
     alg_bytes = 2.0 * esz * slab_voxels  # state read + state (or sdf) write per voxel per pass (2*s B/voxel)
     achieved = alg_bytes / (mean_pass_ms * 1e-3) / 1e9 if mean_pass_ms else None
-    traffic = ncu_traffic()
+    traffic = ncu_traffic(n, world)
 
     # ---- end to end through the reference-facing C-ABI call, host buffers, copies inside the timed region
     e2e = None
@@ -287,6 +288,34 @@ def run_ours(args):
         e2e = {"value": n ** 3 * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / args.steps * 1e3, "stages_ms": capi.last_timing(),
                "api": "vpb_pipeline_host (pinned host buffers)"}
+
+    if world > 1 and n <= 1024:
+        # every rank: its own pinned host buffers, mesh upload, slab pipeline, download of ITS slab of the sdf and the
+        # occupancy words over its own PCIe link (SlabPipeline.run_host); device-event timed, max over ranks
+        pv = [torch.from_numpy(np.ascontiguousarray(v, np.float32)).pin_memory() for v, _ in meshes]
+        pt = [torch.from_numpy(np.ascontiguousarray(t, np.uint32).view(np.int32)).pin_memory() for _, t in meshes]
+        host_meshes = list(zip(pv, pt))
+        sdf_host = torch.empty(pipe.slab_voxels, dtype=torch.float32).pin_memory()
+        words_host = torch.empty(pipe.grid_slab.numel(), dtype=torch.int32).pin_memory()
+        for _ in range(max(1, min(args.warmup, 2))):
+            pipe.run_host(host_meshes, op=op, sdf_out=sdf_host, words_out=words_host)
+        barrier()
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            pipe.run_host(host_meshes, op=op, sdf_out=sdf_host, words_out=words_host)
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item()) * 1e-3
+        h2d = sum(v.numel() * 4 + t_.numel() * 4 for v, t_ in host_meshes) * world
+        d2h = n ** 3 * 4 + capi.n_words(n) * 4
+        e2e = {"value": n ** 3 * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / args.steps * 1e3,
+               "api": f"SlabPipeline.run_host on {world} ranks (pinned host buffers; every rank uploads the meshes and "
+                      "downloads its own z-slab of the sdf + occupancy)"}
 
     if rank != 0:
         if world > 1:

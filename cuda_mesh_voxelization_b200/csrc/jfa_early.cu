@@ -24,6 +24,8 @@
 //
 // Multi-GPU: a rank owning the z-slab [z0, z1) runs every lattice (it has the full occupancy grid) and stores only
 // its slab -- the three passes that would otherwise need whole remote slabs (k >= slab thickness) need no exchange.
+// Each pass only produces the lattice planes the slab's result depends on (see lo1 / hi1 in the kernel): with 8 slabs
+// the last pass (the one with the longest seed list) pushes to 1 plane of 8, the middle one to 3 of 8.
 #include "common.cuh"
 
 #include <cmath>
@@ -88,6 +90,13 @@ jfa_early(const EarlyArgs a) {
     const uint32_t n = a.n, K = a.K;
     const uint32_t rx0 = blockIdx.x * G, ry = blockIdx.y, rz = blockIdx.z;
     const float* __restrict__ lut = a.lut;
+    // Slab runs only need the lattice planes l with rz + l K in [z0, z1) at the end.  The pass with lattice stride S
+    // reads sources S planes away, so its targets are needed on [lo1 - (S - 1), hi1 + (S - 1)] (S = 1, 2, 4: margins 0,
+    // 1 = the S=1 reach, 3 = the S=1 and S=2 reaches): pushes to other planes are skipped, their points never get a key,
+    // drop out of the next pass's list and are never stored.  With the whole grid (z0 = 0, z1 = n) every range is [0, 7].
+    const int lo1 = a.z0 > rz ? (int)((a.z0 - rz + K - 1u) / K) : 0;
+    const int hi1 = a.z1 > rz ? min(L - 1, (int)((a.z1 - 1u - rz) / K)) : -1;
+    if (lo1 > hi1) return;                                 // no plane of this lattice lies in the slab (uniform per CTA)
     if (tid == 0) s_count = 0;
     __syncthreads();
 
@@ -138,23 +147,26 @@ jfa_early(const EarlyArgs a) {
     for (int S = 4; S >= 1; S >>= 1) {
         __syncthreads();                                   // state, keys and list of this pass are in place
         const int count = s_count;
+        const int nlo = max(0, lo1 - (S - 1)), nspan = min(L - 1, hi1 + (S - 1)) - nlo;   // target planes this pass: nlo .. nlo + nspan
         // push: every point that holds a seed offers it to itself (code 0) and to its <= 26 lattice neighbours
 #pragma unroll 1
         for (int e = tid; e < count; e += THREADS) {
             const int p = list[e];
             const int g = p % G, q = p / G;
             const int i = q & 7, j = (q >> 3) & 7, l = q >> 6;
+            bool xo[3], yo[3], zo[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) zo[d] = (unsigned)(l + (d - 1) * S - nlo) <= (unsigned)nspan;
+            if (!(zo[0] || zo[1] || zo[2])) continue;      // a source none of whose z-targets is needed
             const state_t s = st[p];
             const float sx = __ldg(lut + jfa_x(s)), sy = __ldg(lut + MAXN + jfa_y(s)), sz = __ldg(lut + 2 * MAXN + jfa_z(s));
             const int x = (int)(rx0 + g) + i * (int)K, y = (int)ry + j * (int)K, z = (int)rz + l * (int)K;
             const int kk = S * (int)K;
             float X[3], Y[3], Z[3];
-            bool xo[3], yo[3], zo[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 xo[d] = (unsigned)(i + (d - 1) * S) < (unsigned)L;
                 yo[d] = (unsigned)(j + (d - 1) * S) < (unsigned)L;
-                zo[d] = (unsigned)(l + (d - 1) * S) < (unsigned)L;
                 X[d] = sqdiff(sx, __ldg(lut + (xo[d] ? x + (d - 1) * kk : x)));
                 Y[d] = sqdiff(sy, __ldg(lut + MAXN + (yo[d] ? y + (d - 1) * kk : y)));
                 Z[d] = sqdiff(sz, __ldg(lut + 2 * MAXN + (zo[d] ? z + (d - 1) * kk : z)));
@@ -183,11 +195,13 @@ jfa_early(const EarlyArgs a) {
 #pragma unroll
         for (int m = 0; m < QPT; ++m) {
             const int p = 4 * (tid + m * THREADS);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fresh[m][u] = 0;
+            if ((unsigned)(p / (L * L * G) - nlo) > (unsigned)nspan) continue;   // plane not produced by this pass (warp-uniform)
             const uint4 k4 = *reinterpret_cast<const uint4*>(key + p);
             const uint32_t kq[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                fresh[m][u] = 0;
                 if (kq[u] == NOKEY) continue;
                 held |= 1u << (4 * m + u);
                 const uint32_t code = kq[u] & 31u;
@@ -203,6 +217,7 @@ jfa_early(const EarlyArgs a) {
 #pragma unroll
         for (int m = 0; m < QPT; ++m) {
             const int p = 4 * (tid + m * THREADS);
+            if ((unsigned)(p / (L * L * G) - nlo) > (unsigned)nspan) continue;   // its keys were never touched and never will be
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((moved >> (4 * m + u)) & 1u) st[p + u] = fresh[m][u];

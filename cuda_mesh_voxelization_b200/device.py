@@ -37,6 +37,15 @@ class DeviceMesh:
         # uint32 indices travel as int32 bit patterns (torch has no first-class uint32 storage ops)
         self.tris = torch.from_numpy(np.ascontiguousarray(tris, np.uint32).view(np.int32)).to(device)
 
+    @classmethod
+    def empty(cls, n_verts, n_tris, device):
+        """Uninitialised device buffers of a mesh's size (filled by stream-ordered copies from pinned host memory)."""
+        self = cls.__new__(cls)
+        self.n_verts, self.n_tris = int(n_verts), int(n_tris)
+        self.verts = torch.empty((self.n_verts, 3), dtype=torch.float32, device=device)
+        self.tris = torch.empty((self.n_tris, 3), dtype=torch.int32, device=device)
+        return self
+
     @property
     def nbytes(self):
         return self.n_verts * 12 + self.n_tris * 12
