@@ -60,6 +60,7 @@ struct F4Args {
     int k;
     int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
     int lz, segs_z;           // outputs per march segment, segments per z-lattice column
+    int res_z, cols;          // z residues (= z-lattice columns) in the slab; consecutive columns walked by one CTA
     int tiles_y;              // TR-row tiles per y-lattice column
     uint32_t key_base;        // bits subtracted from every distance: (E0 << 23)
     uint32_t key_k0;          // -(key_base * 16) mod 2^32
@@ -100,6 +101,9 @@ __device__ __forceinline__ void ldg_pair(const uint64_t* p, uint64_t& a, uint64_
 }
 __device__ __forceinline__ void st_pair(uint32_t* p, uint32_t a, uint32_t b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
 __device__ __forceinline__ void st_pair(uint64_t* p, uint64_t a, uint64_t b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
+
+constexpr int M_ALL = 0, M_FIRST = 1, M_LAST = 2;
+template <int M> struct Mode { static constexpr int value = M; };
 
 // running winner of one output plane for the thread's 2 rows x 2 voxels
 struct Acc {
@@ -147,11 +151,8 @@ struct Flood4 {
         }
         // ---- tile coordinates ---------------------------------------------------------------------------------
         const int xs = blockIdx.x * SEG;
-        const int rz = blockIdx.z / a.segs_z, sz = blockIdx.z - rz * a.segs_z;
-        const int zl0 = rz + sz * a.lz * k;                       // slab-local z of the first output plane
-        int steps = 0;
-        if (zl0 < (int)a.T) steps = min(a.lz, ((int)a.T - zl0 + k - 1) / k);
-        if (steps == 0) return;
+        const int rzg = blockIdx.z / a.segs_z, sz = blockIdx.z - rzg * a.segs_z;
+        int zl0 = 0, steps = 0;                                    // set per z-lattice column below
         const int ry = blockIdx.y / a.tiles_y, ty = blockIdx.y - ry * a.tiles_y;
         const int gy0 = ry + (ty * TR + 2 * warp) * k;             // the thread's rows: gy0 and gy0 + k
         const bool ok[2] = {gy0 < n, gy0 + k < n};
@@ -247,14 +248,15 @@ struct Flood4 {
         };
 
         Acc acc[3];
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) { acc[s].key[r][0] = acc[s].key[r][1] = NONE; acc[s].tag[r][0] = acc[s].tag[r][1] = 0u; }
 
         // one input plane p: candidates dz=-1 of output p+1 (accN), dz=0 of output p (accC), dz=+1 of output p-1 (accP),
         // then output p-1 is complete and written.
-        auto step = [&](int p, Acc& accN, Acc& accC, Acc& accP) {
+        // `mode` (compile time): ALL, or one of the two planes at the ends of a march, which feed ONE output plane only:
+        // FIRST = plane -1 (only the dz=-1 group of output 0), LAST = plane `steps` (only the dz=+1 group of output steps-1).
+        auto step = [&](auto mode, int p, Acc& accN, Acc& accC, Acc& accP) {
+            constexpr int M = decltype(mode)::value;
+            constexpr bool T0 = M != M_LAST, T1 = M == M_ALL, T2 = M != M_FIRST;   // which targets this plane feeds
+            constexpr bool TT[3] = {T0, T1, T2};
             const bool in_grid = plane_in_grid(p);
             if (ok[0] && in_grid) {
                 const float* fb = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW + tbase;
@@ -277,7 +279,8 @@ struct Flood4 {
                         const float2 X = sq2(__fadd2_rn(fx[c], nqx), nz);          // (sx - qx)^2, shared by both rows
                         float2 Z[3];
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) Z[t] = sq2(__fadd2_rn(fz[c], nq[t]), nz);   // shared by both rows
+                        for (int t = 0; t < 3; ++t)
+                            if (TT[t]) Z[t] = sq2(__fadd2_rn(fz[c], nq[t]), nz);   // shared by both rows
 #pragma unroll
                         for (int r2 = 0; r2 < 2; ++r2) {
                             const int r = rho - r2;                 // candidate row relative to voxel row r2
@@ -286,6 +289,7 @@ struct Flood4 {
                             const uint32_t kc = a.key_k0 + (uint32_t)(r * 4 + c);
 #pragma unroll
                             for (int t = 0; t < 3; ++t) {
+                                if (!TT[t]) continue;
                                 const float2 d = __fadd2_rn(xy, Z[t]);   // ((dx*dx)+(dy*dy)) + (dz*dz)
                                 kk[r2][t][c][0] = __float_as_uint(d.x) * 16u + kc;
                                 kk[r2][t][c][1] = __float_as_uint(d.y) * 16u + kc;
@@ -307,6 +311,7 @@ struct Flood4 {
                         for (int t = 0; t < 3; ++t)
 #pragma unroll
                             for (int v = 0; v < 2; ++v) {
+                                if (!TT[t]) continue;
                                 uint32_t(&q)[3][2] = kk[r2][t];
                                 uint32_t& gg = g[r2][t][v];
                                 if (r == 0) {
@@ -335,24 +340,26 @@ struct Flood4 {
 #pragma unroll
                     for (int v = 0; v < 2; ++v) {
                         // output p+1: this plane is its first group
-                        accN.key[r2][v] = g[r2][0][v];
-                        accN.tag[r2][v] = tag;
+                        if (T0) {
+                            accN.key[r2][v] = g[r2][0][v];
+                            accN.tag[r2][v] = tag;
+                        }
                         // output p: own seed first (keeps ties against the dz=-1 group), then this plane's 8 neighbours
-                        {
+                        if (T1) {
                             const bool prev_wins = (accC.key[r2][v] | 15u) < ownk[r2][v];
                             accC.key[r2][v] = prev_wins ? accC.key[r2][v] : ownk[r2][v];
                             accC.tag[r2][v] = prev_wins ? accC.tag[r2][v] : tag;
+                            merge(accC.key[r2][v], accC.tag[r2][v], g[r2][1][v], tag);
                         }
-                        merge(accC.key[r2][v], accC.tag[r2][v], g[r2][1][v], tag);
                         // output p-1: last group
-                        merge(accP.key[r2][v], accP.tag[r2][v], g[r2][2][v], tag);
+                        if (T2) merge(accP.key[r2][v], accP.tag[r2][v], g[r2][2][v], tag);
                     }
-            } else if (ok[0]) {
+            } else if (ok[0] && T0) {
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) accN.key[r2][0] = accN.key[r2][1] = NONE;   // no dz=-1 group for output p+1
             }
             // ---- output plane p-1 is complete ---------------------------------------------------------------------
-            if (p >= 1) {
+            if (T2 && p >= 1) {
                 const int zl = zl0 + (p - 1) * k;
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
@@ -384,27 +391,56 @@ struct Flood4 {
             }
         };
 
-        // ---- march: planes p = -1 .. steps ------------------------------------------------------------------------
-        if (plane_in_grid(-1)) { fetch(-1); stage(-1); }
+        // ---- march: planes p = -1 .. steps of every z-lattice column this CTA walks ----------------------------------------
         int p = -1;
-        auto iteration = [&](Acc& accN, Acc& accC, Acc& accP) {
+        auto iteration = [&](auto mode, Acc& accN, Acc& accC, Acc& accP) {
             __syncthreads();                                       // plane p staged by everyone (NBUF 2: plane p-1 consumed)
             const bool more = p < steps && plane_in_grid(p + 1);
             if (more) fetch(p + 1);
-            step(p, accN, accC, accP);
+            step(mode, p, accN, accC, accP);
             if (C::NBUF == 1) __syncthreads();                     // plane p consumed before it is overwritten
             if (more) stage(p + 1);
             ++p;
         };
 #pragma unroll 1
-        while (true) {
-            // slot of output o is (o + 1) % 3; p = -1 + 3m here
-            iteration(acc[1], acc[0], acc[2]);
-            if (p > steps) break;
-            iteration(acc[2], acc[1], acc[0]);
-            if (p > steps) break;
-            iteration(acc[0], acc[2], acc[1]);
-            if (p > steps) break;
+        for (int ci = 0; ci < a.cols; ++ci) {
+            const int rz = rzg * a.cols + ci;
+            if (rz >= a.res_z) break;
+            zl0 = rz + sz * a.lz * k;                              // slab-local z of the first output plane
+            if (zl0 >= (int)a.T) break;                            // (later columns start even higher)
+            steps = min(a.lz, ((int)a.T - zl0 + k - 1) / k);
+            if (ci > 0) __syncthreads();                           // the previous column's last plane has been consumed
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { acc[s].key[r][0] = acc[s].key[r][1] = NONE; acc[s].tag[r][0] = acc[s].tag[r][1] = 0u; }
+            if (plane_in_grid(-1)) { fetch(-1); stage(-1); }
+            p = -1;
+            // slot of output o is (o + 1) % 3
+            iteration(Mode<M_FIRST>{}, acc[1], acc[0], acc[2]);    // p = -1: first group of output 0
+#pragma unroll 1
+            while (true) {
+                if (p >= steps) break;
+                iteration(Mode<M_ALL>{}, acc[2], acc[1], acc[0]);  // p = 0 (mod 3)
+                if (p >= steps) break;
+                iteration(Mode<M_ALL>{}, acc[0], acc[2], acc[1]);  // p = 1 (mod 3)
+                if (p >= steps) break;
+                iteration(Mode<M_ALL>{}, acc[1], acc[0], acc[2]);  // p = 2 (mod 3)
+            }
+            // p == steps: last group of output steps-1, whose slot is steps % 3
+            {
+                const int slot = steps % 3;
+                Acc last;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        last.key[r][v] = slot == 0 ? acc[0].key[r][v] : (slot == 1 ? acc[1].key[r][v] : acc[2].key[r][v]);
+                        last.tag[r][v] = slot == 0 ? acc[0].tag[r][v] : (slot == 1 ? acc[1].tag[r][v] : acc[2].tag[r][v]);
+                    }
+                __syncthreads();                                   // plane `steps` staged by everyone
+                step(Mode<M_LAST>{}, p, last, last, last);
+            }
         }
     }
 };
@@ -464,7 +500,11 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
     const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
     const int tr = cy >= 16 ? 16 : 8;
     a.tiles_y = (cy + tr - 1) / tr;
-    dim3 grid(n / SEG, res_y * a.tiles_y, res_z * a.segs_z);
+    // short marches (thin slabs, large k): one CTA walks several z-lattice columns, so the tables, the staging offsets and
+    // the pipeline fill are paid once per CTA instead of once per 2-4 output planes
+    a.res_z = (int)res_z;
+    a.cols = (a.contiguous && a.lz < 8) ? (8 / a.lz < (int)res_z ? 8 / a.lz : (int)res_z) : 1;
+    dim3 grid(n / SEG, res_y * a.tiles_y, ((res_z + a.cols - 1) / a.cols) * a.segs_z);
     VPB_REQUIRE(grid.y <= 65535u && grid.z <= 65535u, "jfa_pass: grid too large (k=%u)", k);
     const bool fin = sdf != nullptr;
     if (tr == 8) {
