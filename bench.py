@@ -238,6 +238,15 @@ def run_ours(args):
     ms_total = float(ms.item())
     launches = capi.kernel_launches() - launches0
 
+    partition_label = None
+    if world > 1:
+        halo = {"push": "halo planes written into the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
+                        "device-side barrier per pass",
+                "pull": "halo planes read from the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
+                        "device-side barrier per pass"}.get(pipe.dma, "NCCL send/recv halo exchange per pass")
+        early = ("fused early passes work-shared (each rank 1/N of the lattices, stored into the owners' slabs over NVLink)"
+                 if pipe.dma and getattr(pipe, "dist_early", False) else "fused early passes run per rank, exchange-free")
+        partition_label = f"{halo}; {early}"
     # dominant kernel: the JFA flood pass (all but the cheap first passes run ~the same code at full density)
     pass_ms = {}
     for k, a, b in pipe.pass_events:
@@ -336,6 +345,7 @@ def run_ours(args):
                          f"voxelization + OpenMP CSG + OpenMP JFA, {dt:.2f} s"}
 
     value = n ** 3 * args.steps / (ms_total * 1e-3) / 1e9
+    transport = partition_label
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -343,7 +353,7 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": args.op,
                    "l2": f"per-step working set (2 x {esz * n ** 3 / 1e9:.1f} GB seed state + {4 * n ** 3 / 1e9:.1f} GB sdf) "
                          ">> 126 MB L2, no flush needed",
-                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, NCCL halo exchange per pass",
+                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, {transport}",
                    **({"stage_ms_rank0": stage_ms} if stage_ms else {}),
                    **({"stage_ms_by_rank": stage_ranks} if stage_ranks else {})},
         "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the flood passes of a step: k = N/16 .. 1 when the "

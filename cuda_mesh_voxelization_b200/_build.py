@@ -44,6 +44,21 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
         return os.environ["VPB_LIB"]
     if out is None and not force and not _stale():
         return LIB
+    if out is None:
+        # one builder at a time (torchrun starts one process per GPU): the others wait, then find the library fresh
+        import fcntl
+        with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if not force and not _stale():
+                    return LIB
+                return _build_locked(verbose, extra_flags, None)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
+    return _build_locked(verbose, extra_flags, out)
+
+
+def _build_locked(verbose, extra_flags, out):
     nvcc = _nvcc()
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     objdir = os.path.join(PKG, "build") if out is None else out + ".obj"
@@ -67,10 +82,12 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{log}")
     target = LIB if out is None else out
-    link = [nvcc, "-ccbin", host_cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs]
+    tmp = f"{target}.tmp{os.getpid()}"          # linked under another name and renamed: a reader never sees half a file
+    link = [nvcc, "-ccbin", host_cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, target)
     return target
 
 

@@ -41,6 +41,8 @@ SIGNATURES = [
     ("vpb_jfa_early_supported", ctypes.c_int, [ctypes.c_uint32, ctypes.c_float, _f32p]),
     ("vpb_jfa_early_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, _f32p,
                                          _vp, _vp, _vp]),
+    ("vpb_jfa_early_dist_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_uint32, _vp, ctypes.c_uint32, _vp, _vp]),
     ("vpb_jfa_pass_dev", ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.c_float, _f32p, _vp, _vp, _vp, _vp]),
     ("vpb_jfa_pass_peer_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_uint32, ctypes.c_uint32,

@@ -254,6 +254,18 @@ int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint3
                      stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
+int vpb_jfa_early_dist_dev(const uint32_t* words_full, uint32_t n, float vs, const float origin[3], uint32_t rz_lo,
+                           uint32_t rz_hi, uint32_t slab_planes, uint32_t* const* slab_states, uint32_t world,
+                           uint32_t* shell_scratch, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && words_full && shell_scratch && slab_states, "jfa_early_dist: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN, "jfa_early_dist: bad n=%u", n);
+    const Frame f = make_frame(n, vs, origin);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
+    return jfa_state64(n) ? jfa_early_dist_launch_s64(words_full, f, rz_lo, rz_hi, slab_planes, slab_states, world, shell_scratch, st)
+                          : jfa_early_dist_launch(words_full, f, rz_lo, rz_hi, slab_planes, slab_states, world, shell_scratch, st);
+}
+
 int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, uint32_t n,
                      uint32_t z0, uint32_t z1, uint32_t k, float vs, const float origin[3], const uint32_t* words_full,
                      float* sdf, uint32_t* seeds, void* stream) {

@@ -132,6 +132,10 @@ int jfa_early_supported(const Frame& f);
 int jfa_early_supported_s64(const Frame& f);
 int jfa_early_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
                          uint32_t* state, cudaStream_t st);
+int jfa_early_dist_launch(const uint32_t* words_full, const Frame& f, uint32_t rz_lo, uint32_t rz_hi, uint32_t slab_planes,
+                          uint32_t* const* slab_states, uint32_t world, uint32_t* shell_scratch, cudaStream_t st);
+int jfa_early_dist_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t rz_lo, uint32_t rz_hi, uint32_t slab_planes,
+                              uint32_t* const* slab_states, uint32_t world, uint32_t* shell_scratch, cudaStream_t st);
 // the same three with the 64-bit state (N <= 2048); state pointers are uint64_t* behind the uint32_t* of the C ABI
 int jfa_seed_launch_s64(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_pass_launch_s64(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,

@@ -50,6 +50,11 @@ struct EarlyArgs {
     const float* lut;         // px | py | pz
     uint32_t n, K, z0, z1;
     uint32_t key_base;
+    // distributed mode (T != 0): this launch runs the z residues rz0 .. rz0 + gridDim.z - 1 completely and stores every
+    // plane z into the slab of its owner, rank z / T, at dst_rank[z / T] (device addresses valid in THIS process: the
+    // owners' buffers mapped over NVLink); z0 = 0, z1 = n
+    uint32_t rz0, T;
+    state_t* dst_rank[8];
 };
 
 __device__ __forceinline__ float sqdiff(float s, float q) {
@@ -88,7 +93,7 @@ jfa_early(const EarlyArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = a.n, K = a.K;
-    const uint32_t rx0 = blockIdx.x * G, ry = blockIdx.y, rz = blockIdx.z;
+    const uint32_t rx0 = blockIdx.x * G, ry = blockIdx.y, rz = blockIdx.z + a.rz0;
     const float* __restrict__ lut = a.lut;
     // Slab runs only need the lattice planes l with rz + l K in [z0, z1) at the end.  The pass with lattice stride S
     // reads sources S planes away, so its targets are needed on [lo1 - (S - 1), hi1 + (S - 1)] (S = 1, 2, 4: margins 0,
@@ -237,19 +242,24 @@ jfa_early(const EarlyArgs a) {
         if (z < a.z0 || z >= a.z1) continue;
         state_t v[4];
         ld4(st + p, v);
-        st4(a.dst + ((size_t)(z - a.z0) * n + y) * n + x, v);
+        if (a.T) {
+            const uint32_t owner = z / a.T;
+            st4(a.dst_rank[owner] + ((size_t)(z - owner * a.T) * n + y) * n + x, v);    // 7 of 8 planes: a store over NVLink
+        } else {
+            st4(a.dst + ((size_t)(z - a.z0) * n + y) * n + x, v);
+        }
     }
 }
 
 template <int G, int THREADS>
-int launch(const EarlyArgs& a, cudaStream_t st) {
+int launch(const EarlyArgs& a, uint32_t n_rz, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)PTS * G * (sizeof(state_t) + 4 + 2);
     static bool configured = false;
     if (!configured) {
         VPB_CUDA(cudaFuncSetAttribute(jfa_early<G, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         configured = true;
     }
-    dim3 grid(a.K / G, a.K, a.K);
+    dim3 grid(a.K / G, a.K, n_rz);
     jfa_early<G, THREADS><<<grid, THREADS, SMEM, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;
@@ -324,11 +334,41 @@ int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32
     a.shell = shell_scratch;
     a.dst = reinterpret_cast<state_t*>(state_);
     a.n = n; a.z0 = z0; a.z1 = z1;
+    a.rz0 = 0; a.T = 0;
+    for (auto& d : a.dst_rank) d = nullptr;
     a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
     const char* env = getenv("VPB_JFA_EARLY");
     const bool g16 = env && strcmp(env, "16") == 0 && a.K % 16u == 0;
-    return g16 ? launch<16, 512>(a, st) : launch<8, 256>(a, st);
+    return g16 ? launch<16, 512>(a, a.K, st) : launch<8, 256>(a, a.K, st);
+}
+
+// Multi-GPU, work-sharing form: this rank runs only the lattices with z residue in [rz_lo, rz_hi) -- all of their planes --
+// and stores plane z into slab_states[z / slab_planes] (rank z / slab_planes's slab of the result, mapped into this
+// process).  Every rank calls it with its own residue range; after a barrier every slab is complete.  The per-lattice
+// work is then done once per job instead of once per rank.  Same return convention as jfa_early_launch.
+int VPB_SFX(jfa_early_dist_launch)(const uint32_t* words_full, const Frame& f, uint32_t rz_lo, uint32_t rz_hi,
+                                   uint32_t slab_planes, uint32_t* const* slab_states, uint32_t world,
+                                   uint32_t* shell_scratch, cudaStream_t st) {
+    const uint32_t n = f.n;
+    EarlyArgs a;
+    if (!early_supported(f, &a.key_base)) return 1;
+    VPB_REQUIRE(words_full && shell_scratch && slab_states, "jfa_early_dist: null buffer");
+    VPB_REQUIRE(world >= 1 && world <= 8 && slab_planes * world == n, "jfa_early_dist: %u slabs of %u planes do not tile N=%u", world, slab_planes, n);
+    a.K = n / 8u;
+    VPB_REQUIRE(rz_lo < rz_hi && rz_hi <= a.K, "jfa_early_dist: bad residue range [%u,%u) of %u", rz_lo, rz_hi, a.K);
+    for (uint32_t r = 0; r < 8; ++r) {
+        a.dst_rank[r] = r < world ? reinterpret_cast<state_t*>(slab_states[r]) : nullptr;
+        if (r < world) VPB_REQUIRE(slab_states[r] && (reinterpret_cast<uintptr_t>(slab_states[r]) & 15u) == 0, "jfa_early_dist: slab %u unaligned", r);
+    }
+    { const int rc = shell_launch(words_full, n, shell_scratch, st); if (rc != VPB_OK) return rc; }
+    a.shell = shell_scratch;
+    a.dst = nullptr;
+    a.n = n; a.z0 = 0; a.z1 = n;
+    a.rz0 = rz_lo; a.T = slab_planes;
+    a.lut = VPB_SFX(jfa_lut_launch)(f, st);
+    if (!a.lut) return VPB_ERR_CUDA;
+    return launch<8, 256>(a, rz_hi - rz_lo, st);
 }
 
 }  // namespace vpb

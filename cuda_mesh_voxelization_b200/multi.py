@@ -166,14 +166,14 @@ class SlabPipeline:
         self.dma = False
         if not self.peer:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
-            want_dma = (comm is None and world > 1 and os.environ.get("VPB_HALO", "dma") != "nccl"
+            want_dma = (comm is None and world > 1 and os.environ.get("VPB_HALO", "push") != "nccl"
                         and all(k < p.T for k in self.steps))
             if want_dma:
                 try:
                     self._setup_dma()
-                    self.dma = True
+                    self.dma = "push" if os.environ.get("VPB_HALO", "push") in ("push", "dma") else "pull"
                 except Exception as e:  # no symmetric-memory support on this box: NCCL halo exchange instead
-                    if os.environ.get("VPB_HALO") == "dma":
+                    if os.environ.get("VPB_HALO") in ("dma", "push", "pull"):
                         raise
                     import sys
                     print(f"[vpb200] symmetric-memory halo pull unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
@@ -224,6 +224,12 @@ class SlabPipeline:
         self.symm = [symm_mem.rendezvous(t, dist.group.WORLD) for t in self.ext]
         self.peer_ext = [[h.get_buffer(r, (total,), torch.int32) if r != p.rank else self.ext[i] for r in range(p.world)]
                          for i, h in enumerate(self.symm)]
+        import os
+        # the fused early kernel in work-sharing form (each rank 1/world of the lattices, results stored straight into the
+        # owners' slabs over NVLink) needs the slabs mapped everywhere, i.e. this mode; VPB_EARLY_DIST=0 turns it off
+        self.dist_early = (self.use_early and (self.n // 8) % p.world == 0 and os.environ.get("VPB_EARLY_DIST", "1") != "0")
+        self.side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.side_done = [torch.cuda.Event() for _ in range(2)]
 
     def peer_barrier(self, i):
         """All ranks have finished what they launched so far on buffer pair i (device-side, on the current stream)."""
@@ -291,6 +297,20 @@ class SlabPipeline:
         if rc != 0:
             self.capi.check(rc if rc < 0 else -1)
 
+    def early_dist(self, slab_ptrs):
+        """Work-sharing form of early(): this rank runs the lattices whose z residue lies in its 1/world share of
+        [0, N/8) and stores every plane into its owner's buffer-1 centre (`slab_ptrs[r]`: rank r's centre, mapped into
+        this process).  The caller puts a barrier across the ranks after it."""
+        p, K = self.plan, self.n // 8
+        share = K // p.world
+        table = (ctypes.c_void_p * p.world)(*slab_ptrs)
+        scratch = self.center(0)
+        assert scratch.numel() * 4 >= self.capi.n_words(self.n) * 4, "state slab smaller than the bit grid"
+        rc = self.lib.vpb_jfa_early_dist_dev(_ptr(self.grid_full), self.n, self.vs, self._o(), p.rank * share,
+                                             (p.rank + 1) * share, p.T, table, p.world, _ptr(scratch), self._stream())
+        if rc != 0:
+            self.capi.check(rc if rc < 0 else -1)
+
     def exchange(self, k, cur):
         """Halo exchange for step k on the current state buffer `cur` (0/1)."""
         p = self.plan
@@ -299,14 +319,45 @@ class SlabPipeline:
         if self.peer:
             self.peer_barrier(cur)      # everyone's previous pass (which wrote buffer `cur`) is complete and visible
             return
+        src_center = self.center(cur)
         if self.dma:
-            # everyone's previous pass (which wrote buffer `cur`) is complete; then pull the neighbours' boundary planes.
-            # The buffer a neighbour pulls from is next overwritten two passes later, after the next barrier, which this
-            # rank only reaches (stream order) once its own pulls are done.
+            torch = self.torch
+            main = torch.cuda.current_stream()
+
+            def on_side_streams(copies):
+                """The (at most two) neighbour copies run concurrently on two side streams, forked from and joined back
+                into the current stream with events."""
+                fork = torch.cuda.Event()
+                fork.record(main)
+                for i, (dst, src) in enumerate(copies):
+                    st = self.side[i]
+                    st.wait_event(fork)
+                    with torch.cuda.stream(st):
+                        dst.copy_(src, non_blocking=True)
+                        self.side_done[i].record(st)
+                    main.wait_event(self.side_done[i])
+
+            if self.dma == "push":
+                # write my boundary planes into the neighbours' halo regions, then the barrier: after it every rank's
+                # halos are complete.  A neighbour's halo of this buffer was last read two passes ago, before the
+                # barrier that preceded my previous pass.
+                copies = []
+                for t in p.sends(k):
+                    lo = (p.H - k) * self.plane if t.role == "below" else (p.H + p.T) * self.plane
+                    copies.append((self.peer_ext[cur][t.peer][lo:lo + k * self.plane],
+                                   src_center[t.src_lo * self.plane:(t.src_lo + t.count) * self.plane]))
+                on_side_streams(copies)
+                self.symm[cur].barrier(channel=0)
+                return
+            # pull: everyone's previous pass (which wrote buffer `cur`) is complete; then read the neighbours' boundary
+            # planes.  The buffer a neighbour pulls from is next overwritten two passes later, after the next barrier,
+            # which this rank only reaches (stream order) once its own pulls are done.
             self.symm[cur].barrier(channel=0)
+            copies = []
             for t in p.recvs(k):
                 lo = (p.H + t.src_lo) * self.plane
-                self.halo(cur, t.role, k).copy_(self.peer_ext[cur][t.peer][lo:lo + t.count * self.plane])
+                copies.append((self.halo(cur, t.role, k), self.peer_ext[cur][t.peer][lo:lo + t.count * self.plane]))
+            on_side_streams(copies)
             return
         src = self.center(cur)
 
@@ -384,6 +435,7 @@ class SlabPipeline:
         self._mark(record_passes, "allgather_bits")
         if not sdf:
             return
+        p_ = self.plan
         if self.use_early:
             if self.peer:
                 self.peer_barrier(0)          # buffer 0 is about to become scratch: nobody may still be reading it
@@ -391,7 +443,12 @@ class SlabPipeline:
                 e0 = self.torch.cuda.Event(enable_timing=True)
                 e1 = self.torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self.early()
+            if self.dma and self.dist_early:
+                off = p_.H * self.plane * 4
+                self.early_dist([t.data_ptr() + off for t in self.peer_ext[1]])
+                self.symm[1].barrier(channel=0)    # every rank's share has landed in every slab
+            else:
+                self.early()
             if record_passes:
                 e1.record()
                 self.early_events.append((e0, e1))
@@ -434,8 +491,9 @@ class SlabPipeline:
 class LocalComm:
     """All ranks in one process / on one GPU: exchanges become device copies.  Drives the ranks in lockstep."""
 
-    def __init__(self):
+    def __init__(self, dist_early=False):
         self.ranks: List[SlabPipeline] = []
+        self.dist_early = dist_early
 
     def add(self, p: SlabPipeline):
         self.ranks.append(p)
@@ -454,8 +512,13 @@ class LocalComm:
             for q in R:
                 w = q.grid_slab.numel()
                 p.grid_full[q.plan.rank * w:(q.plan.rank + 1) * w].copy_(q.grid_slab)
-        for p in R:
-            p.early() if p.use_early else p.seed()
+        if self.dist_early and R[0].use_early and (R[0].n // 8) % len(R) == 0:
+            ptrs = [q.center(1).data_ptr() for q in R]       # all slabs on this GPU: the work-sharing early kernel, emulated
+            for p in R:
+                p.early_dist(ptrs)
+        else:
+            for p in R:
+                p.early() if p.use_early else p.seed()
         cur = 1 if R[0].use_early else 0
         for k in R[0].steps:
             for p in R:                                   # every receive pulls from the sender's current centre

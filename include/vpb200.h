@@ -115,6 +115,14 @@ VPB_API int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0
 VPB_API int vpb_jfa_early_supported(uint32_t n, float voxel_size, const float origin[3]);
 VPB_API int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
                               const float origin[3], uint32_t* shell_scratch, uint32_t* state_slab, void* stream);
+/* The same kernel, work-sharing form for multi-GPU runs whose result slabs are mapped into every process (symmetric
+ * memory over NVLink): the caller runs only the lattices with z residue (z mod N/8) in [rz_lo, rz_hi) -- all eight planes of
+ * each -- and plane z is stored into slab_states[z / slab_planes] (r < world <= 8; slab_planes * world == N; addresses valid
+ * in THIS process, 16-byte aligned).  Every rank calls it with its own residue range; after a barrier across the ranks
+ * every slab holds the state after the passes k = N/2, N/4, N/8.  Returns like vpb_jfa_early_dev. */
+VPB_API int vpb_jfa_early_dist_dev(const uint32_t* words_full, uint32_t n, float voxel_size, const float origin[3],
+                                   uint32_t rz_lo, uint32_t rz_hi, uint32_t slab_planes, uint32_t* const* slab_states,
+                                   uint32_t world, uint32_t* shell_scratch, void* stream);
 /* One flood pass with step k over slab [z0,z1).  src_below/src_mid/src_above point at the state of plane
  * (z0 - k), z0 and (z0 + k) respectively, each followed by the next (z1-z0-1) planes; planes outside the grid
  * are never dereferenced, so the pointer may be anything there.  On one GPU: mid = in, below = in - k*N*N,

@@ -328,8 +328,9 @@ def test_device_pipeline_matches_host_pipeline(golden, meshes, oracle, vpb):
     assert all(a.elapsed_time(b) > 0 for _, a, b in pipe.pass_events)
 
 
+@pytest.mark.parametrize("dist_early", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_z_slabs_are_bit_identical_to_one_gpu(world, meshes, oracle, vpb):
+def test_z_slabs_are_bit_identical_to_one_gpu(world, dist_early, meshes, oracle, vpb):
     """The multi-GPU code path (slab voxelization, halo / far-slab sources, slab-local marches) emulated with all
     slabs on one GPU: the concatenated slab outputs must equal the single-GPU result and the oracle."""
     import torch
@@ -340,7 +341,9 @@ def test_z_slabs_are_bit_identical_to_one_gpu(world, meshes, oracle, vpb):
     names = ["bimba", "bunny"]
     origin, vs = _frame(oracle, meshes, names, n)
     dm = [DeviceMesh(*meshes[m], "cuda:0") for m in names]
-    comm = LocalComm()
+    # dist_early: the fused early kernel in its work-sharing form (vpb_jfa_early_dist_dev: every rank 1/world of the
+    # lattices, planes stored into their owners' slabs), all slabs being on this one GPU
+    comm = LocalComm(dist_early=dist_early)
     for r in range(world):
         comm.add(SlabPipeline(n, vs, origin, r, world, comm=comm))
     sdf = comm.run_all(dm, op=capi.OP_DIFFERENCE)
