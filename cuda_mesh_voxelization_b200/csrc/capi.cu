@@ -50,6 +50,9 @@ struct Context {
     int device = 0;
     int sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // D2H of finished z-chunks of the sdf while the final pass still runs
+    cudaEvent_t chunk_ev[16] = {};
+    cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float timing[3] = {0, 0, 0};
     Buf verts, tris, grid_a, grid_b, scratch, state_a, state_b, sdf, seeds;
@@ -94,11 +97,19 @@ int finalize_any(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1
                             : jfa_finalize_launch(state, f, z0, z1, words, sdf, seeds, st);
 }
 
+// Where the host-buffer calls want the result: the final pass is then issued in z-chunks and every finished chunk of the
+// signed distance (and of the seed indices) starts its D2H copy on a second stream while the next chunk is computed.
+struct HostSink {
+    float* sdf_host = nullptr;
+    uint32_t* seeds_host = nullptr;
+    cudaEvent_t kernels_done = nullptr;           // recorded on the compute stream after the last chunk's kernel
+};
+
 // Runs seed extraction + all passes + signed output on one GPU.  sdf may be NULL: the final pass never writes its
 // state destination, so the signed distance then goes INTO that free state buffer (4 B/voxel of HBM saved; at 2048^3
 // that is what makes the job fit one GPU) and *sdf_at tells the caller where it is.
 int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st,
-            float** sdf_at = nullptr) {
+            float** sdf_at = nullptr, const HostSink* sink = nullptr) {
     const uint32_t n = f.n;
     // seed extraction + the passes k = N/2, N/4, N/8 fused (jfa_early.cu; the shell bits go through the free buffer sb),
     // or, for shapes it does not take, seed extraction and every pass on its own
@@ -121,6 +132,35 @@ int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, f
         const bool last = (k == 1);
         float* target = sdf ? sdf : reinterpret_cast<float*>(out);
         if (last && sdf_at) *sdf_at = target;
+        if (last && sink && n >= 256) {
+            // final pass in z-chunks; chunk c's D2H overlaps chunk c+1's kernel (the copies are all enqueued after the
+            // kernels, so a pageable destination, whose copies block the host, cannot delay a launch)
+            const uint32_t chunks = 8, tc = (n + chunks - 1) / chunks;
+            const size_t plane_vox = (size_t)n * n;
+            uint32_t used = 0;
+            for (uint32_t z0 = 0; z0 < n; z0 += tc, ++used) {
+                const uint32_t z1 = z0 + tc < n ? z0 + tc : n;
+                char* mid = in + (uint64_t)z0 * plane_bytes;
+                VPB_TRY(pass_any(reinterpret_cast<uint32_t*>(mid - plane_bytes), reinterpret_cast<uint32_t*>(mid),
+                                 reinterpret_cast<uint32_t*>(mid + plane_bytes),
+                                 reinterpret_cast<uint32_t*>(out + (uint64_t)z0 * plane_bytes), f, z0, z1, 1, words,
+                                 target + z0 * plane_vox, seeds ? seeds + z0 * plane_vox : nullptr, st));
+                VPB_CUDA(cudaEventRecord(g_ctx.chunk_ev[used], st));
+            }
+            if (sink->kernels_done) VPB_CUDA(cudaEventRecord(sink->kernels_done, st));
+            used = 0;
+            for (uint32_t z0 = 0; z0 < n; z0 += tc, ++used) {
+                const uint32_t z1 = z0 + tc < n ? z0 + tc : n;
+                const size_t off = z0 * plane_vox, cnt = (size_t)(z1 - z0) * plane_vox;
+                VPB_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, g_ctx.chunk_ev[used], 0));
+                VPB_CUDA(cudaMemcpyAsync(sink->sdf_host + off, target + off, cnt * 4, cudaMemcpyDeviceToHost, g_ctx.copy_stream));
+                if (seeds && sink->seeds_host)
+                    VPB_CUDA(cudaMemcpyAsync(sink->seeds_host + off, seeds + off, cnt * 4, cudaMemcpyDeviceToHost, g_ctx.copy_stream));
+            }
+            VPB_CUDA(cudaEventRecord(g_ctx.copy_done, g_ctx.copy_stream));
+            VPB_CUDA(cudaStreamWaitEvent(st, g_ctx.copy_done, 0));
+            return VPB_OK;
+        }
         VPB_TRY(pass_any(reinterpret_cast<uint32_t*>(in - k * plane_bytes), reinterpret_cast<uint32_t*>(in),
                          reinterpret_cast<uint32_t*>(in + k * plane_bytes), reinterpret_cast<uint32_t*>(out), f, 0, n, k, words,
                          last ? target : nullptr, last ? seeds : nullptr, st));
@@ -176,7 +216,10 @@ int vpb_init(int device) {
     g_ctx.sms = prop.multiProcessorCount;
     g_ctx.device = device;
     VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     for (auto& ev : g_ctx.ev) VPB_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : g_ctx.chunk_ev) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    VPB_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_done, cudaEventDisableTiming));
     g_ctx.ready = true;
     g_launches = 0;
     return VPB_OK;
@@ -190,6 +233,12 @@ void vpb_shutdown(void) {
                    &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds})
         b->release();
     for (auto& ev : g_ctx.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : g_ctx.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    if (g_ctx.copy_done) cudaEventDestroy(g_ctx.copy_done);
+    g_ctx.copy_done = nullptr;
+    cudaStreamSynchronize(g_ctx.copy_stream);
+    cudaStreamDestroy(g_ctx.copy_stream);
+    g_ctx.copy_stream = nullptr;
     cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
     g_ctx.ready = false;
@@ -372,6 +421,9 @@ int vpb_csg_host(uint32_t* a, const uint32_t* b, uint32_t n, int op) {
     return finish_timing();
 }
 
+// grids for which jfa_run issues the final pass in z-chunks with overlapped D2H (must match the test inside jfa_run)
+static bool sink_takes(uint32_t n) { return n >= 256 && n / 2 != 0; }
+
 // two state buffers; the signed distance is written into whichever of them the final pass leaves free (jfa_run)
 static int reserve_jfa(uint32_t n, bool want_seeds) {
     const size_t vox = (size_t)n * n * n;
@@ -395,11 +447,17 @@ int vpb_jfa_host(const uint32_t* words, uint32_t n, float vs, const float origin
     VPB_CUDA(cudaMemcpyAsync(g_ctx.grid_a.p, words, nw * 4, cudaMemcpyHostToDevice, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
     float* sdf_dev = nullptr;
+    const bool chunked = sink_takes(n);
+    HostSink sink;
+    sink.sdf_host = sdf_out; sink.seeds_host = seeds_out; sink.kernels_done = g_ctx.ev[2];
     VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), make_frame(n, vs, origin), g_ctx.state_a.as<uint32_t>(),
-                    g_ctx.state_b.as<uint32_t>(), nullptr, seeds_out ? g_ctx.seeds.as<uint32_t>() : nullptr, st, &sdf_dev));
-    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
-    VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
-    if (seeds_out) VPB_CUDA(cudaMemcpyAsync(seeds_out, g_ctx.seeds.p, vox * 4, cudaMemcpyDeviceToHost, st));
+                    g_ctx.state_b.as<uint32_t>(), nullptr, seeds_out ? g_ctx.seeds.as<uint32_t>() : nullptr, st, &sdf_dev,
+                    chunked ? &sink : nullptr));
+    if (!chunked) {
+        VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+        VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
+        if (seeds_out) VPB_CUDA(cudaMemcpyAsync(seeds_out, g_ctx.seeds.p, vox * 4, cudaMemcpyDeviceToHost, st));
+    }
     VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
     return finish_timing();
 }
@@ -434,12 +492,16 @@ int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n
         if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(g_ctx.grid_a.as<uint32_t>(), g_ctx.grid_b.as<uint32_t>(), nw, op, st));
     }
     float* sdf_dev = nullptr;
-    if (sdf_out)
+    const bool chunked = sdf_out && sink_takes(n);
+    if (sdf_out) {
+        HostSink sink;
+        sink.sdf_host = sdf_out; sink.kernels_done = g_ctx.ev[2];
         VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(),
-                        nullptr, nullptr, st, &sdf_dev));
-    VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
+                        nullptr, nullptr, st, &sdf_dev, chunked ? &sink : nullptr));
+    }
+    if (!chunked) VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
     if (words_out) VPB_CUDA(cudaMemcpyAsync(words_out, g_ctx.grid_a.p, nw * 4, cudaMemcpyDeviceToHost, st));
-    if (sdf_out) VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
+    if (sdf_out && !chunked) VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
     return finish_timing();
 }
