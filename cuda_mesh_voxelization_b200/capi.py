@@ -15,7 +15,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 _vp = ctypes.c_void_p
 
 OP_VOID, OP_UNION, OP_INTERSECTION, OP_DIFFERENCE = 0, 1, 2, 3
-MODE_SOLID, MODE_SURFACE = 0, 1
+MODE_SOLID, MODE_SURFACE, MODE_SURFACE_CONSERVATIVE = 0, 1, 2
 
 # every symbol vpb200.h declares: (name, restype, argtypes)
 SIGNATURES = [
@@ -34,6 +34,9 @@ SIGNATURES = [
     ("vpb_voxelize_scratch_bytes", ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]),
     ("vpb_voxelize_dev", ctypes.c_int, [_vp, ctypes.c_uint64, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
                                         _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_size_t, _vp]),
+    ("vpb_voxelize_surface_scratch_bytes", ctypes.c_size_t, [ctypes.c_uint64]),
+    ("vpb_voxelize_surface_dev", ctypes.c_int, [_vp, ctypes.c_uint64, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
+                                                _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_size_t, _vp]),
     ("vpb_csg_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_int, _vp]),
     ("vpb_shell_dev", ctypes.c_int, [_vp, ctypes.c_uint32, _vp, _vp]),
     ("vpb_jfa_state_bytes", ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),

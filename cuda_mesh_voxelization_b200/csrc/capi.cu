@@ -3,6 +3,7 @@
 // Replaces the reference's per-call CudaPtr<T> malloc/copy/free pattern (vplib/src/cuda_ptr.h:14-93,
 // e.g. vox/naive.cu:91-121, jfa/tiled.cu:250-336) with one stream, grow-only device buffers that survive
 // between calls, and stage-to-stage device residency inside vpb_pipeline_host.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -268,6 +269,17 @@ int vpb_voxelize_dev(const float* verts, uint64_t n_verts, const uint32_t* tris,
     return vox_launch(verts, n_verts, tris, n_tris, make_frame(n, vs, origin), z0, z1, words_slab, scratch, scratch_bytes, st);
 }
 
+size_t vpb_voxelize_surface_scratch_bytes(uint64_t n_tris) { return vox_surface_scratch_bytes(n_tris); }
+
+int vpb_voxelize_surface_dev(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, uint32_t n, float vs,
+                             const float origin[3], uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch,
+                             size_t scratch_bytes, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin, "voxelize_surface: null origin");
+    return vox_surface_launch(verts, n_verts, tris, n_tris, make_frame(n, vs, origin), z0, z1, words_slab, scratch, scratch_bytes,
+                              stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
 int vpb_csg_dev(uint32_t* a, const uint32_t* b, uint64_t n_words, int op, void* stream) {
     VPB_TRY(require_ready());
     return csg_launch(a, b, n_words, op, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
@@ -378,19 +390,23 @@ int vpb_voxelize_host(const float* verts, uint64_t n_verts, const uint32_t* tris
                       const float origin[3], int mode, uint32_t* words_out) {
     VPB_TRY(require_ready());
     VPB_REQUIRE(words_out && origin && n > 0, "voxelize: bad argument");
-    VPB_REQUIRE(mode == VPB_MODE_SOLID || mode == VPB_MODE_SURFACE, "voxelize: bad mode %d", mode);
+    VPB_REQUIRE(mode == VPB_MODE_SOLID || mode == VPB_MODE_SURFACE || mode == VPB_MODE_SURFACE_CONSERVATIVE, "voxelize: bad mode %d", mode);
     VPB_REQUIRE(n_tris == 0 || (verts && tris), "voxelize: null mesh");
     cudaStream_t st = g_ctx.stream;
     const uint64_t nw = grid_words(n);
-    const size_t sb = vox_scratch_bytes(n, n_tris, 0, n);
+    const size_t sb = std::max(vox_scratch_bytes(n, n_tris, 0, n), vox_surface_scratch_bytes(n_tris));
     VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
     VPB_TRY(g_ctx.scratch.reserve(sb));
     if (mode == VPB_MODE_SURFACE) VPB_TRY(g_ctx.grid_b.reserve(nw * 4 + 16));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
     VPB_TRY(upload_mesh(verts, n_verts, tris, n_tris, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
-    VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts, g_ctx.tris.as<uint32_t>(), n_tris, make_frame(n, vs, origin), 0, n,
-                       g_ctx.grid_a.as<uint32_t>(), g_ctx.scratch.p, g_ctx.scratch.cap, st));
+    if (mode == VPB_MODE_SURFACE_CONSERVATIVE)
+        VPB_TRY(vox_surface_launch(g_ctx.verts.as<float>(), n_verts, g_ctx.tris.as<uint32_t>(), n_tris, make_frame(n, vs, origin),
+                                   0, n, g_ctx.grid_a.as<uint32_t>(), g_ctx.scratch.p, g_ctx.scratch.cap, st));
+    else
+        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts, g_ctx.tris.as<uint32_t>(), n_tris, make_frame(n, vs, origin), 0, n,
+                           g_ctx.grid_a.as<uint32_t>(), g_ctx.scratch.p, g_ctx.scratch.cap, st));
     const uint32_t* result = g_ctx.grid_a.as<uint32_t>();
     if (mode == VPB_MODE_SURFACE) {
         VPB_TRY(shell_launch(g_ctx.grid_a.as<uint32_t>(), n, g_ctx.grid_b.as<uint32_t>(), st));

@@ -114,6 +114,9 @@ __device__ __forceinline__ uint32_t interior_mask32(const uint32_t* __restrict__
 size_t vox_scratch_bytes(uint32_t n, uint64_t n_tris, uint32_t z0, uint32_t z1);
 int vox_launch(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, const Frame& f,
                uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t vox_surface_scratch_bytes(uint64_t n_tris);
+int vox_surface_launch(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, const Frame& f,
+                       uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch, size_t scratch_bytes, cudaStream_t st);
 int csg_launch(uint32_t* a, const uint32_t* b, uint64_t n_words, int op, cudaStream_t st);
 int shell_launch(const uint32_t* words, uint32_t n, uint32_t* shell, cudaStream_t st);
 int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);

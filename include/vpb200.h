@@ -44,7 +44,10 @@ enum { VPB_OP_VOID = 0, VPB_OP_UNION = 1, VPB_OP_INTERSECTION = 2, VPB_OP_DIFFER
 /* Voxelization mode.  SOLID == the reference's X-ray parity fill (vplib/src/vox/sequential.cpp:16-57).
  * SURFACE == the seed shell of the solid (set voxels with an empty or out-of-grid 26-neighbour,
  * vplib/src/jfa/sequential.cpp:36-60) — the only surface set the reference defines. */
-enum { VPB_MODE_SOLID = 0, VPB_MODE_SURFACE = 1 };
+enum { VPB_MODE_SOLID = 0, VPB_MODE_SURFACE = 1, VPB_MODE_SURFACE_CONSERVATIVE = 2 };
+/* SURFACE_CONSERVATIVE == every voxel whose closed box meets a triangle (Schwarz & Seidel 2010, section 4.1 triangle/box
+ * overlap: plane/box test + three projected edge-function tests).  The reference has no such voxelizer (its README names
+ * one, no source does), so this mode is pinned only against oracle/vp_oracle.c vpo_voxelize_surface. */
 
 /* ---- lifetime -------------------------------------------------------------------------------
  * Replaces the implicit context the reference sets up with cudaSetDevice(0) (apps/cli/main.cpp:22-23)
@@ -96,6 +99,12 @@ VPB_API size_t vpb_voxelize_scratch_bytes(uint32_t n, uint64_t n_tris, uint32_t 
 VPB_API int vpb_voxelize_dev(const float* verts_xyz, uint64_t n_verts, const uint32_t* tri_idx, uint64_t n_tris,
                              uint32_t n, float voxel_size, const float origin[3], uint32_t z0, uint32_t z1,
                              uint32_t* words_slab, void* scratch, size_t scratch_bytes, void* stream);
+/* Conservative surface voxelization of slab [z0,z1) (VPB_MODE_SURFACE_CONSERVATIVE); words_slab is overwritten.
+ * scratch: vpb_voxelize_surface_scratch_bytes(n_tris) bytes. */
+VPB_API size_t vpb_voxelize_surface_scratch_bytes(uint64_t n_tris);
+VPB_API int vpb_voxelize_surface_dev(const float* verts_xyz, uint64_t n_verts, const uint32_t* tri_idx, uint64_t n_tris,
+                                     uint32_t n, float voxel_size, const float origin[3], uint32_t z0, uint32_t z1,
+                                     uint32_t* words_slab, void* scratch, size_t scratch_bytes, void* stream);
 VPB_API int vpb_csg_dev(uint32_t* a_inout, const uint32_t* b, uint64_t n_words, int op, void* stream);
 /* shell_out = seed shell of `words` (full N^3 grid), both dense bit grids. */
 VPB_API int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell_out, void* stream);

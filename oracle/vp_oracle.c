@@ -269,3 +269,98 @@ VPO_API int vpo_jfa(const uint32_t* words, uint32_t n_, float vs, const float* o
     free(px); free(sdf_a); free(sdf_b); free(seed_a); free(seed_b);
     return 0;
 }
+
+/* ---------------------------------------------------------------- conservative surface voxelization
+ * NO REFERENCE COUNTERPART (the reference's README mentions surface voxelization, no source implements it:
+ * SURVEY §8 a11) => PARITY UNPINNED for this function: it is the executable spec of
+ * cuda_mesh_voxelization_b200/csrc/vox_surface.cu, checked in tests/test_oracle_golden.py against an independent
+ * float64 separating-axis test.  Algorithm: Schwarz & Seidel 2010, section 4.1 (triangle/box overlap = plane/box test
+ * + three projected edge-function tests); voxel (ix,iy,iz) is the closed box [p, p+vs]^3, p = origin + (float)i * vs.
+ * Every operation below is one binary32 rounding, in the order the CUDA kernel uses.  ORs into words_slab (zero-filled
+ * here), the slab [z0,z1) of a dense vplib bit grid. */
+static inline float pos0f(float x) { return x > 0.0f ? x : 0.0f; }
+
+static void surf_edges(float* ea, float* eb, float* ed, int proj, float s, const float* va, const float* vb,
+                       const float* e_a, const float* e_b, float vs) {
+    for (int i = 0; i < 3; ++i) {
+        float na = -e_b[i] * s, nb = e_a[i] * s;
+        float m1 = na * va[i], m2 = nb * vb[i];
+        float dot = m1 + m2;
+        float t1 = vs * na, t2 = vs * nb;
+        float acc = -dot + pos0f(t1);
+        ea[proj * 3 + i] = na;
+        eb[proj * 3 + i] = nb;
+        ed[proj * 3 + i] = acc + pos0f(t2);
+    }
+}
+
+VPO_API int vpo_voxelize_surface(const float* verts, uint64_t n_verts, const uint32_t* idx, uint64_t n_tris, uint32_t n,
+                                 float vs, const float* origin, uint32_t z0, uint32_t z1, uint32_t* words_slab) {
+    if (!n || z0 >= z1 || z1 > n || !(vs > 0.0f)) return -1;
+    (void)n_verts;
+    const uint64_t N = n;
+    memset(words_slab, 0, ((N * N * (z1 - z0) + 31u) / 32u) * 4u);
+    for (uint64_t t = 0; t < n_tris; ++t) {
+        float vx[3], vy[3], vz[3], ex[3], ey[3], ez[3];
+        for (int i = 0; i < 3; ++i) {
+            const float* v = verts + 3ull * idx[3 * t + i];
+            vx[i] = v[0]; vy[i] = v[1]; vz[i] = v[2];
+        }
+        for (int i = 0; i < 3; ++i) {
+            int j = (i + 1) % 3;
+            ex[i] = vx[j] - vx[i]; ey[i] = vy[j] - vy[i]; ez[i] = vz[j] - vz[i];
+        }
+        float a1 = ey[0] * ez[1], a2 = ez[0] * ey[1]; float nx = a1 - a2;
+        float b1 = ez[0] * ex[1], b2 = ex[0] * ez[1]; float ny = b1 - b2;
+        float c1 = ex[0] * ey[1], c2 = ey[0] * ex[1]; float nz = c1 - c2;
+        if ((nx == 0.0f && ny == 0.0f && nz == 0.0f) || nx != nx || ny != ny || nz != nz) continue;
+        float cx = nx > 0.0f ? vs : 0.0f, cy = ny > 0.0f ? vs : 0.0f, cz = nz > 0.0f ? vs : 0.0f;
+        float p1 = nx * (cx - vx[0]), p2 = ny * (cy - vy[0]), p3 = nz * (cz - vz[0]);
+        float s12 = p1 + p2; float d1 = s12 + p3;
+        float q1 = nx * ((vs - cx) - vx[0]), q2 = ny * ((vs - cy) - vy[0]), q3 = nz * ((vs - cz) - vz[0]);
+        float t12 = q1 + q2; float d2 = t12 + q3;
+        float ea[9], eb[9], ed[9];
+        surf_edges(ea, eb, ed, 0, nz >= 0.0f ? 1.0f : -1.0f, vx, vy, ex, ey, vs);
+        surf_edges(ea, eb, ed, 1, nx >= 0.0f ? 1.0f : -1.0f, vy, vz, ey, ez, vs);
+        surf_edges(ea, eb, ed, 2, ny >= 0.0f ? 1.0f : -1.0f, vz, vx, ez, ex, vs);
+        const float* vv[3] = {vx, vy, vz};
+        int lo[3], hi[3], ok = 1;
+        for (int a = 0; a < 3; ++a) {
+            float mn = fminf(vv[a][0], fminf(vv[a][1], vv[a][2])), mx = fmaxf(vv[a][0], fmaxf(vv[a][1], vv[a][2]));
+            float dlo = mn - origin[a], dhi = mx - origin[a];
+            float flo = floorf(dlo / vs), fhi = floorf(dhi / vs);
+            if (flo != flo || fhi != fhi) { ok = 0; break; }
+            float nmax = (float)n;
+            lo[a] = (int)fminf(fmaxf(flo, -1.0f), nmax);
+            hi[a] = (int)fminf(fmaxf(fhi, -1.0f), nmax);
+            int cl = a == 2 ? (int)z0 : 0, ch = a == 2 ? (int)z1 - 1 : (int)n - 1;
+            if (lo[a] < cl) lo[a] = cl;
+            if (hi[a] > ch) hi[a] = ch;
+        }
+        if (!ok) continue;
+        for (int iz = lo[2]; iz <= hi[2]; ++iz)
+            for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                for (int ix = lo[0]; ix <= hi[0]; ++ix) {
+                    float mx_ = (float)ix * vs, my_ = (float)iy * vs, mz_ = (float)iz * vs;
+                    float px = origin[0] + mx_, py = origin[1] + my_, pz = origin[2] + mz_;
+                    float n1 = nx * px, n2 = ny * py, n3 = nz * pz;
+                    float n12 = n1 + n2; float np = n12 + n3;
+                    float l = np + d1, r = np + d2;
+                    float prod = l * r;
+                    if (prod > 0.0f) continue;
+                    const float pa[3] = {px, py, pz}, pb[3] = {py, pz, px};
+                    int out = 0;
+                    for (int proj = 0; proj < 3 && !out; ++proj)
+                        for (int i = 0; i < 3; ++i) {
+                            float u = ea[proj * 3 + i] * pa[proj], w = eb[proj * 3 + i] * pb[proj];
+                            float uw = u + w;
+                            float e = uw + ed[proj * 3 + i];
+                            if (e < 0.0f) { out = 1; break; }
+                        }
+                    if (out) continue;
+                    uint64_t bit = ((uint64_t)(iz - (int)z0) * N + (uint64_t)iy) * N + (uint64_t)ix;
+                    words_slab[bit >> 5] |= 1u << (bit & 31u);
+                }
+    }
+    return 0;
+}

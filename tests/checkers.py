@@ -57,6 +57,8 @@ class Oracle:
         L.vpo_frame.argtypes = [_f32p, ctypes.c_uint64, ctypes.c_uint32, _f32p, _f32p]
         L.vpo_voxelize.argtypes = [_f32p, ctypes.c_uint64, _u32p, ctypes.c_uint64, ctypes.c_uint32,
                                    ctypes.c_float, _f32p, _u32p, _u64p]
+        L.vpo_voxelize_surface.argtypes = [_f32p, ctypes.c_uint64, _u32p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
+                                           _f32p, ctypes.c_uint32, ctypes.c_uint32, _u32p]
         L.vpo_csg.argtypes = [_u32p, _u32p, ctypes.c_uint32, ctypes.c_int]
         L.vpo_seed_shell.argtypes = [_u32p, ctypes.c_uint32, _u32p]
         L.vpo_jfa.argtypes = [_u32p, ctypes.c_uint32, ctypes.c_float, _f32p, _f32p, _u64p]
@@ -89,6 +91,18 @@ class Oracle:
                                    _fp(origin), _up(words), stats.ctypes.data_as(_u64p))
         assert rc == 0
         return (words, stats) if return_stats else words
+
+    def voxelize_surface(self, verts, tris, n, vs, origin, z0=0, z1=None):
+        """Conservative surface voxelization (Schwarz-Seidel triangle/box overlap) of the slab [z0, z1)."""
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        tris = np.ascontiguousarray(tris, dtype=np.uint32)
+        origin = np.ascontiguousarray(origin, dtype=np.float32)
+        z1 = n if z1 is None else z1
+        words = np.zeros((n * n * (z1 - z0) + 31) // 32, np.uint32)
+        rc = self.lib.vpo_voxelize_surface(_fp(verts), verts.shape[0], _up(tris), tris.shape[0], n, float(vs), _fp(origin),
+                                           z0, z1, _up(words))
+        assert rc == 0
+        return words
 
     def csg(self, a, b, n, op):
         a = np.array(a, dtype=np.uint32, copy=True)

@@ -397,3 +397,88 @@ def test_full_size_1024_properties(meshes, oracle, vpb):
         # (5) every returned seed is a shell voxel
         sl_lin = sx + n * (sy + n * sz)
         assert bool(torch.all(((shell[sl_lin >> 5] >> (sl_lin & 31).to(torch.int32)) & 1) == 1))
+
+
+def test_slab_pipeline_run_host_matches_reference_digest(golden, meshes, oracle, vpb):
+    """SlabPipeline.run_host (what bench.py's multi-GPU e2e leg calls on every rank): pinned host meshes in, the rank's
+    slab of the sdf and of the occupancy words out.  One rank owning the whole grid must reproduce config 2's digests."""
+    import torch
+    from cuda_mesh_voxelization_b200.multi import SlabPipeline
+    rec = golden["bimba_union_bunny_n256"]
+    n = rec["n"]
+    origin, vs = _frame(oracle, meshes, rec["meshes"], n)
+    pipe = SlabPipeline(n, vs, origin, 0, 1)
+    host = [(torch.from_numpy(np.ascontiguousarray(meshes[m][0], np.float32)).pin_memory(),
+             torch.from_numpy(np.ascontiguousarray(meshes[m][1], np.uint32).view(np.int32)).pin_memory()) for m in rec["meshes"]]
+    sdf = torch.empty(pipe.slab_voxels, dtype=torch.float32).pin_memory()
+    words = torch.empty(pipe.grid_slab.numel(), dtype=torch.int32).pin_memory()
+    for _ in range(2):                      # the second call reuses the device mesh buffers
+        pipe.run_host(host, op=rec["op"], sdf_out=sdf, words_out=words)
+        torch.cuda.synchronize()
+        assert f"{oracle.fnv(words.numpy().view(np.uint32)):016x}" == rec["result"]["fnv"]
+        assert f"{oracle.fnv(sdf.numpy()):016x}" == rec["sdf"]["fnv"]
+
+
+# ---------------------------------------------------------------------------------------------- conservative surface mode
+
+@pytest.mark.parametrize("mesh,n", [("d20", 32), ("d20", 128), ("sphere", 33), ("torus", 64), ("bunny", 100), ("bimba", 128),
+                                    ("bunny", 256)])
+def test_conservative_surface_matches_spec(mesh, n, meshes, oracle, vpb):
+    """VPB_MODE_SURFACE_CONSERVATIVE (csrc/vox_surface.cu, Schwarz-Seidel triangle/box overlap) against its executable
+    spec oracle.voxelize_surface, bit for bit (the reference has no surface voxelizer; the spec itself is pinned
+    against a float64 separating-axis test in tests/test_oracle_golden.py).  d20 at 128^3 has 20 large triangles:
+    the queued, CTA-per-triangle path."""
+    from cuda_mesh_voxelization_b200 import capi
+    v, t = meshes[mesh]
+    origin, vs = oracle.frame(v, n)
+    got = vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE_CONSERVATIVE)
+    want = oracle.voxelize_surface(v, t, n, vs, origin)
+    assert oracle.popcount(want) > 0
+    assert np.array_equal(got, want)
+    # every voxel that holds a vertex is set
+    idx = np.floor((v - origin) / vs).astype(np.int64)
+    idx = idx[np.all((idx >= 0) & (idx < n), axis=1)]
+    lin = idx[:, 0] + n * (idx[:, 1] + n * idx[:, 2])
+    assert np.all((got[lin >> 5] >> (lin & 31).astype(np.uint32)) & 1)
+
+
+def test_conservative_surface_clipped_frame_and_slabs(meshes, oracle, vpb):
+    """A frame that cuts the mesh (boxes outside the grid are skipped) and the slab form of the device call."""
+    import ctypes
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    v, t = meshes["sphere"]
+    n = 64
+    origin = np.array([-0.4, -0.6, -0.2], np.float32)
+    vs = np.float32(0.02)
+    want = oracle.voxelize_surface(v, t, n, vs, origin)
+    assert np.array_equal(vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE_CONSERVATIVE), want)
+    lib = capi.load()
+    dm = DeviceMesh(v, t, "cuda:0")
+    scratch = torch.empty(int(lib.vpb_voxelize_surface_scratch_bytes(dm.n_tris)), dtype=torch.uint8, device="cuda")
+    parts = []
+    for z0, z1 in [(0, 16), (16, 48), (48, 64)]:
+        out = torch.empty(n * n * (z1 - z0) // 32, dtype=torch.int32, device="cuda")
+        capi.check(lib.vpb_voxelize_surface_dev(ctypes.c_void_p(dm.verts.data_ptr()), dm.n_verts, ctypes.c_void_p(dm.tris.data_ptr()),
+                                                dm.n_tris, n, float(vs), origin.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                                z0, z1, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()),
+                                                scratch.numel(), None))
+        torch.cuda.synchronize()
+        parts.append(out.cpu().numpy().view(np.uint32))
+        assert np.array_equal(parts[-1], oracle.voxelize_surface(v, t, n, vs, origin, z0, z1))
+    assert np.array_equal(np.concatenate(parts), want)
+
+
+def test_conservative_surface_benchmark_mesh_1024(meshes, oracle, vpb):
+    """Full size: the 1 348 128-face bunny at 1024^3 against the spec (one second of CPU), plus a sanity relation with the
+    seed shell of the solid (the conservative surface is a thicker set than half the shell)."""
+    from cuda_mesh_voxelization_b200 import capi, meshgen
+    v, t = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
+    n = 1024
+    origin, vs = oracle.frame(v, n)
+    got = vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE_CONSERVATIVE)
+    want = oracle.voxelize_surface(v, t, n, vs, origin)
+    assert np.array_equal(got, want)
+    shell = vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE)
+    assert oracle.popcount(got) * 2 >= oracle.popcount(shell)

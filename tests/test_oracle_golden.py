@@ -83,3 +83,60 @@ def test_oracle_vs_live_reference_random_frames(meshes, oracle, reference):
         sr = reference.jfa(ra, n, 0.173, o)
         so = oracle.jfa(oa, n, 0.173, o)
         assert np.array_equal(sr.view(np.uint32), so.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- surface voxelizer spec
+
+def _sat_overlap(tri, lo, hi):
+    """Exact (float64) triangle / axis-aligned-box overlap by the separating-axis theorem (13 axes), vectorised over
+    boxes: tri [3,3], lo/hi [M,3] -> bool [M].  Touching counts as overlapping."""
+    c = (lo + hi) * 0.5
+    h = (hi - lo) * 0.5
+    v = tri[None, :, :] - c[:, None, :]                   # [M,3,3]
+    e = np.stack([tri[1] - tri[0], tri[2] - tri[1], tri[0] - tri[2]])
+    axes = [np.eye(3)[i] for i in range(3)] + [np.cross(e[0], e[1])]
+    axes += [np.cross(e[i], np.eye(3)[j]) for i in range(3) for j in range(3)]
+    ok = np.ones(len(c), bool)
+    for a in axes:
+        if not np.any(a):
+            continue
+        p = v @ a                                          # [M,3]
+        r = h @ np.abs(a)
+        ok &= ~((p.min(axis=1) > r) | (p.max(axis=1) < -r))
+    return ok
+
+
+@pytest.mark.parametrize("mesh,n", [("d20", 16), ("torus", 24), ("sphere", 20)])
+def test_surface_voxelizer_spec_against_separating_axis_test(mesh, n, meshes, oracle):
+    """oracle.voxelize_surface (the executable spec of csrc/vox_surface.cu; the reference has no surface voxelizer, so
+    this is its only pin) against an independent float64 SAT: every box that overlaps a triangle even after shrinking
+    by 1e-4 voxels is set, and no box is set that misses every triangle after growing by 1e-4 voxels."""
+    v, t = meshes[mesh]
+    origin, vs = oracle.frame(v, n)
+    words = oracle.voxelize_surface(v, t, n, vs, origin)
+    got = np.unpackbits(words.view(np.uint8), bitorder="little")[:n ** 3].astype(bool)
+    iz, iy, ix = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    idx = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(np.float64)
+    lo = origin.astype(np.float64)[None, :] + idx * float(vs)
+    hi = lo + float(vs)
+    eps = 1e-4 * float(vs)
+    must = np.zeros(n ** 3, bool)
+    may = np.zeros(n ** 3, bool)
+    v64 = v.astype(np.float64)
+    for tri in t[: 400]:                                    # a few hundred triangles are enough to pin the predicate
+        T = v64[tri]
+        bb = np.all((hi >= T.min(axis=0) - 2 * eps) & (lo <= T.max(axis=0) + 2 * eps), axis=1)
+        sel = np.nonzero(bb)[0]
+        must[sel] |= _sat_overlap(T, lo[sel] + eps, hi[sel] - eps)
+        may[sel] |= _sat_overlap(T, lo[sel] - eps, hi[sel] + eps)
+    sub = oracle.voxelize_surface(v, t[: 400], n, vs, origin)
+    got_sub = np.unpackbits(sub.view(np.uint8), bitorder="little")[:n ** 3].astype(bool)
+    assert must.sum() > 0
+    assert not np.any(must & ~got_sub), "a box that overlaps a triangle is not set"
+    assert not np.any(got_sub & ~may), "a box that misses every triangle is set"
+    assert not np.any(got_sub & ~got)                       # more triangles only add voxels
+    # slabs: the two halves of the grid, voxelized separately, concatenate to the whole
+    h = n // 2
+    if (n * n * h) % 32 == 0:
+        parts = [oracle.voxelize_surface(v, t, n, vs, origin, 0, h), oracle.voxelize_surface(v, t, n, vs, origin, h, n)]
+        assert np.array_equal(np.concatenate(parts), words)
