@@ -240,6 +240,22 @@ void Compute(HostVoxelsGrid<T>& grid, const Mesh& mesh) {
         vplib_b200::print_stage("B200Vox::Processing", t[1]);
     }
 }
+// Extension (vplib has no surface voxelizer, only a README line): grid = the surface of the mesh.  conservative = true:
+// every voxel whose closed box meets a triangle (Schwarz-Seidel triangle/box overlap, VPB_MODE_SURFACE_CONSERVATIVE);
+// false: the seed shell of the solid voxelization, the surface set JFA::Compute starts from (VPB_MODE_SURFACE).
+template <Types type, typename T>
+void ComputeSurface(HostVoxelsGrid<T>& grid, const Mesh& mesh, bool conservative = true) {
+    static_assert(type == Types::B200, "vplib_b200 only provides the B200 back-end (no CPU fallback)");
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "grid word must be uint32_t or uint64_t");
+    VPB_PROFILING_SCOPE("B200VoxSurface(" + mesh.Name + ")");
+    vplib_b200::ensure_init();
+    auto& g = grid.View();
+    vplib_b200::check(vpb_voxelize_host(reinterpret_cast<const float*>(mesh.Coords.data()), mesh.Coords.size(),
+                                        mesh.FacesCoords.data(), mesh.FacesCoords.size() / 3, (uint32_t)g.VoxelsPerSide(),
+                                        g.VoxelSize(), g.Origin(), conservative ? VPB_MODE_SURFACE_CONSERVATIVE : VPB_MODE_SURFACE,
+                                        g.Words32()),
+                      "vpb_voxelize_host", __FILE__, __LINE__);
+}
 // the reference's tiled overload takes a block size first (vox/vox.h:110-111); it has no meaning here
 template <Types type, typename T>
 void Compute(size_t /*blockSize*/, HostVoxelsGrid<T>& grid, const Mesh& mesh) { Compute<type, T>(grid, mesh); }
