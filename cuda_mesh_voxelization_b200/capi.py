@@ -31,6 +31,9 @@ SIGNATURES = [
     ("vpb_jfa_host", ctypes.c_int, [_u32p, ctypes.c_uint32, ctypes.c_float, _f32p, _f32p, _u32p]),
     ("vpb_pipeline_host", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_f32p), _u64p, ctypes.POINTER(_u32p), _u64p,
                                          ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_int, _u32p, _f32p]),
+    ("vpb_pipeline_submit", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_f32p), _u64p, ctypes.POINTER(_u32p), _u64p,
+                                         ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_int, _u32p, _f32p, ctypes.POINTER(ctypes.c_uint64)]),
+    ("vpb_pipeline_wait", ctypes.c_int, [ctypes.c_uint64]),
     ("vpb_voxelize_scratch_bytes", ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]),
     ("vpb_voxelize_dev", ctypes.c_int, [_vp, ctypes.c_uint64, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float,
                                         _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_size_t, _vp]),
@@ -171,3 +174,26 @@ def pipeline_host(meshes, n, voxel_size, origin, op=OP_VOID, want_words=True, wa
     check(load().vpb_pipeline_host(m, vp, nv, tp, nt, n, float(voxel_size), _fp(o), op,
                                    _up(words) if want_words else None, _fp(sdf) if want_sdf else None))
     return words, sdf
+
+
+def pipeline_submit(meshes, n, voxel_size, origin, op=OP_VOID, sdf_out=None, words_out=None):
+    """Asynchronous vpb_pipeline_host: returns (ticket, keepalive).  `meshes` = [(verts float32[V,3], tris uint32[T,3])],
+    `sdf_out` / `words_out` = caller-owned (ideally pinned) arrays; nothing may be touched until pipeline_wait(ticket).
+    `keepalive` holds the argument arrays: keep it until the wait."""
+    vs_ = [np.ascontiguousarray(v, dtype=np.float32) for v, _ in meshes]
+    ts_ = [np.ascontiguousarray(t, dtype=np.uint32) for _, t in meshes]
+    m = len(meshes)
+    vp = (_f32p * m)(*[_fp(v) for v in vs_])
+    tp = (_u32p * m)(*[_up(t) for t in ts_])
+    nv = (ctypes.c_uint64 * m)(*[v.shape[0] for v in vs_])
+    nt = (ctypes.c_uint64 * m)(*[t.shape[0] for t in ts_])
+    o = _origin(origin)
+    ticket = ctypes.c_uint64(0)
+    check(load().vpb_pipeline_submit(m, vp, nv, tp, nt, n, float(voxel_size), _fp(o), op,
+                                     _up(words_out) if words_out is not None else None,
+                                     _fp(sdf_out) if sdf_out is not None else None, ctypes.byref(ticket)))
+    return int(ticket.value), (vs_, ts_, vp, tp, nv, nt, o, sdf_out, words_out)
+
+
+def pipeline_wait(ticket: int) -> None:
+    check(load().vpb_pipeline_wait(ticket))

@@ -57,6 +57,12 @@ struct Context {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float timing[3] = {0, 0, 0};
     Buf verts, tris, grid_a, grid_b, scratch, state_a, state_b, sdf, seeds;
+    // asynchronous pipeline (vpb_pipeline_submit / vpb_pipeline_wait): two jobs in flight, each slot owns the device
+    // copies of its results so that the next job's kernels can run while this one's D2H is still going
+    Buf slot_words[2], slot_sdf[2];
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};
+    uint64_t slot_ticket[2] = {0, 0};             // ticket whose results the slot holds (0 = none)
+    uint64_t next_ticket = 1;
 };
 Context g_ctx;
 
@@ -104,6 +110,8 @@ struct HostSink {
     float* sdf_host = nullptr;
     uint32_t* seeds_host = nullptr;
     cudaEvent_t kernels_done = nullptr;           // recorded on the compute stream after the last chunk's kernel
+    cudaEvent_t copies_done = nullptr;            // non-null: recorded on the copy stream after the last copy and the
+                                                  // compute stream does NOT wait for the copies (asynchronous jobs)
 };
 
 // Runs seed extraction + all passes + signed output on one GPU.  sdf may be NULL: the final pass never writes its
@@ -158,8 +166,12 @@ int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, f
                 if (seeds && sink->seeds_host)
                     VPB_CUDA(cudaMemcpyAsync(sink->seeds_host + off, seeds + off, cnt * 4, cudaMemcpyDeviceToHost, g_ctx.copy_stream));
             }
-            VPB_CUDA(cudaEventRecord(g_ctx.copy_done, g_ctx.copy_stream));
-            VPB_CUDA(cudaStreamWaitEvent(st, g_ctx.copy_done, 0));
+            if (sink->copies_done) {
+                VPB_CUDA(cudaEventRecord(sink->copies_done, g_ctx.copy_stream));
+            } else {
+                VPB_CUDA(cudaEventRecord(g_ctx.copy_done, g_ctx.copy_stream));
+                VPB_CUDA(cudaStreamWaitEvent(st, g_ctx.copy_done, 0));
+            }
             return VPB_OK;
         }
         VPB_TRY(pass_any(reinterpret_cast<uint32_t*>(in - k * plane_bytes), reinterpret_cast<uint32_t*>(in),
@@ -221,6 +233,9 @@ int vpb_init(int device) {
     for (auto& ev : g_ctx.ev) VPB_CUDA(cudaEventCreate(&ev));
     for (auto& ev : g_ctx.chunk_ev) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     VPB_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_done, cudaEventDisableTiming));
+    for (auto& ev : g_ctx.slot_done) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    g_ctx.slot_ticket[0] = g_ctx.slot_ticket[1] = 0;
+    g_ctx.next_ticket = 1;
     g_ctx.ready = true;
     g_launches = 0;
     return VPB_OK;
@@ -230,11 +245,14 @@ void vpb_shutdown(void) {
     if (!g_ctx.ready) return;
     cudaSetDevice(g_ctx.device);
     cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
     for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.scratch, &g_ctx.state_a,
                    &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds})
         b->release();
     for (auto& ev : g_ctx.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : g_ctx.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : g_ctx.slot_done) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (Buf* b : {&g_ctx.slot_words[0], &g_ctx.slot_words[1], &g_ctx.slot_sdf[0], &g_ctx.slot_sdf[1]}) b->release();
     if (g_ctx.copy_done) cudaEventDestroy(g_ctx.copy_done);
     g_ctx.copy_done = nullptr;
     cudaStreamSynchronize(g_ctx.copy_stream);
@@ -520,6 +538,89 @@ int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n
     if (sdf_out && !chunked) VPB_CUDA(cudaMemcpyAsync(sdf_out, sdf_dev, vox * 4, cudaMemcpyDeviceToHost, st));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[3], st));
     return finish_timing();
+}
+
+// ---- asynchronous form of vpb_pipeline_host: up to two jobs in flight ------------------------------------------------
+// Job j's kernels run on the compute stream; every finished z-chunk of its sdf (and its occupancy words) is copied to the
+// host on the copy stream from buffers only job j+2 will reuse, so job j+1's kernels overlap job j's D2H -- the host
+// API is PCIe-bound (4.3 GB of sdf per 1024^3 job), not kernel-bound.
+int vpb_pipeline_submit(int n_meshes, const float* const* verts, const uint64_t* n_verts, const uint32_t* const* tris,
+                        const uint64_t* n_tris, uint32_t n, float vs, const float origin[3], int op, uint32_t* words_out,
+                        float* sdf_out, uint64_t* ticket) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(n_meshes >= 1 && verts && n_verts && tris && n_tris && origin && n > 0 && ticket, "pipeline_submit: bad argument");
+    VPB_REQUIRE(op >= VPB_OP_VOID && op <= VPB_OP_DIFFERENCE, "pipeline_submit: bad op %d", op);
+    VPB_REQUIRE(!sdf_out || n <= 1024, "pipeline_submit: sdf needs N <= 1024 (two result slots must fit the device)");
+    cudaStream_t st = g_ctx.stream, cs = g_ctx.copy_stream;
+    const uint64_t nw = grid_words(n);
+    const size_t vox = (size_t)n * n * n;
+    const Frame f = make_frame(n, vs, origin);
+    const uint64_t t = g_ctx.next_ticket;
+    const int slot = (int)(t & 1u);
+    // the slot's previous job (ticket t-2) must have left the device before its buffers are overwritten
+    if (g_ctx.slot_ticket[slot]) VPB_CUDA(cudaStreamWaitEvent(st, g_ctx.slot_done[slot], 0));
+    uint64_t max_tris = 0;
+    for (int i = 0; i < n_meshes; ++i) max_tris = n_tris[i] > max_tris ? n_tris[i] : max_tris;
+    VPB_TRY(g_ctx.grid_a.reserve(nw * 4 + 16));
+    if (n_meshes > 1) VPB_TRY(g_ctx.grid_b.reserve(nw * 4 + 16));
+    VPB_TRY(g_ctx.scratch.reserve(vox_scratch_bytes(n, max_tris, 0, n)));
+    VPB_TRY(g_ctx.slot_words[slot].reserve(nw * 4 + 16));
+    if (sdf_out) {
+        VPB_TRY(reserve_jfa(n, false));
+        VPB_TRY(g_ctx.slot_sdf[slot].reserve(vox * 4));
+    }
+    uint32_t* words = g_ctx.slot_words[slot].as<uint32_t>();          // grids[0] of this job lives in the slot
+    for (int i = 0; i < n_meshes; ++i) {
+        VPB_TRY(upload_mesh(verts[i], n_verts[i], tris[i], n_tris[i], st));
+        uint32_t* target = i == 0 ? words : g_ctx.grid_b.as<uint32_t>();
+        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts[i], g_ctx.tris.as<uint32_t>(), n_tris[i], f, 0, n, target,
+                           g_ctx.scratch.p, g_ctx.scratch.cap, st));
+        if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(words, g_ctx.grid_b.as<uint32_t>(), nw, op, st));
+    }
+    VPB_CUDA(cudaEventRecord(g_ctx.chunk_ev[15], st));                 // occupancy final
+    bool copies_recorded = false;
+    if (sdf_out) {
+        HostSink sink;
+        sink.sdf_host = sdf_out;
+        sink.copies_done = g_ctx.slot_done[slot];
+        const bool chunked = sink_takes(n);
+        if (words_out && chunked) {                                    // ahead of the sdf chunks on the copy stream
+            VPB_CUDA(cudaStreamWaitEvent(cs, g_ctx.chunk_ev[15], 0));
+            VPB_CUDA(cudaMemcpyAsync(words_out, words, nw * 4, cudaMemcpyDeviceToHost, cs));
+        }
+        VPB_TRY(jfa_run(words, f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(), g_ctx.slot_sdf[slot].as<float>(),
+                        nullptr, st, nullptr, chunked ? &sink : nullptr));
+        copies_recorded = chunked;
+        if (!chunked) {
+            VPB_CUDA(cudaEventRecord(g_ctx.chunk_ev[14], st));
+            VPB_CUDA(cudaStreamWaitEvent(cs, g_ctx.chunk_ev[14], 0));
+            if (words_out) VPB_CUDA(cudaMemcpyAsync(words_out, words, nw * 4, cudaMemcpyDeviceToHost, cs));
+            VPB_CUDA(cudaMemcpyAsync(sdf_out, g_ctx.slot_sdf[slot].p, vox * 4, cudaMemcpyDeviceToHost, cs));
+        }
+    } else if (words_out) {
+        VPB_CUDA(cudaStreamWaitEvent(cs, g_ctx.chunk_ev[15], 0));
+        VPB_CUDA(cudaMemcpyAsync(words_out, words, nw * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    if (!copies_recorded) {
+        VPB_CUDA(cudaStreamWaitEvent(cs, g_ctx.chunk_ev[15], 0));      // also covers "no output requested"
+        VPB_CUDA(cudaEventRecord(g_ctx.slot_done[slot], cs));
+    }
+    g_ctx.slot_ticket[slot] = t;
+    g_ctx.next_ticket = t + 1;
+    *ticket = t;
+    return VPB_OK;
+}
+
+int vpb_pipeline_wait(uint64_t ticket) {
+    VPB_TRY(require_ready());
+    const int slot = (int)(ticket & 1u);
+    VPB_REQUIRE(ticket != 0 && ticket < g_ctx.next_ticket, "pipeline_wait: unknown ticket %llu", (unsigned long long)ticket);
+    // (if the slot has been reused by ticket + 2 the event now marks that later job's copies: waiting for them is
+    // sufficient, the copy stream is in order)
+    VPB_CUDA(cudaEventSynchronize(g_ctx.slot_done[slot]));
+    // kernel errors of the job surface here
+    VPB_CUDA(cudaGetLastError());
+    return VPB_OK;
 }
 
 }  // extern "C"

@@ -88,6 +88,18 @@ VPB_API int vpb_pipeline_host(int n_meshes, const float* const* verts_xyz, const
                               const uint32_t* const* tri_idx, const uint64_t* n_tris, uint32_t n, float voxel_size,
                               const float origin[3], int op, uint32_t* words_out, float* sdf_out);
 
+/* Asynchronous form: enqueue the same work and return at once with a ticket; vpb_pipeline_wait(ticket) returns when the
+ * job's words_out / sdf_out are complete.  Up to two jobs are in flight: the kernels of job j+1 overlap the D2H copy of
+ * job j (the host API is PCIe-bound: 4.3 GB of sdf per 1024^3 job), each job's results living in device buffers that only
+ * job j+2 reuses.  The host buffers of a job (inputs and outputs) must stay valid and untouched until its wait returns;
+ * pinned buffers make the copies truly asynchronous.  Submitting a third job implicitly waits (on the device) for the
+ * first one's copies.  N <= 1024 when sdf_out is given.  No reference counterpart (vplib's Compute calls are synchronous);
+ * bench.py's `e2e` uses it. */
+VPB_API int vpb_pipeline_submit(int n_meshes, const float* const* verts_xyz, const uint64_t* n_verts,
+                                const uint32_t* const* tri_idx, const uint64_t* n_tris, uint32_t n, float voxel_size,
+                                const float origin[3], int op, uint32_t* words_out, float* sdf_out, uint64_t* ticket);
+VPB_API int vpb_pipeline_wait(uint64_t ticket);
+
 /* ---- device-pointer calls: the metric path and the building blocks of the z-slab multi-GPU driver ----
  * All pointers are device pointers in the current context (any allocator, e.g. torch); `stream` is a
  * cudaStream_t (NULL = the library's own stream).  Calls are asynchronous on that stream.

@@ -482,3 +482,31 @@ def test_conservative_surface_benchmark_mesh_1024(meshes, oracle, vpb):
     assert np.array_equal(got, want)
     shell = vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE)
     assert oracle.popcount(got) * 2 >= oracle.popcount(shell)
+
+
+def test_pipeline_submit_wait_overlapped_jobs(golden, meshes, oracle, vpb):
+    """vpb_pipeline_submit / vpb_pipeline_wait: four jobs with different operators submitted back to back (two in flight,
+    slots reused) each reproduce the reference digests of config 2's grid and of the 64^3 cases (non-chunked path)."""
+    import torch
+    for n, names in [(256, ["bimba_union_bunny_n256"] * 3),
+                     (64, ["bimba_union_bunny_n64", "bimba_inter_bunny_n64", "bimba_diff_bunny_n64", "bimba_union_bunny_n64"])]:
+        recs = [golden[k] for k in names]
+        origin, vs = _frame(oracle, meshes, recs[0]["meshes"], n)
+        ms = [meshes[m] for m in recs[0]["meshes"]]
+        outs = [(torch.empty(n ** 3, dtype=torch.float32).pin_memory(), torch.empty((n ** 3 + 31) // 32, dtype=torch.int32).pin_memory())
+                for _ in recs]
+        jobs = []
+        for rec, (sdf, words) in zip(recs, outs):
+            jobs.append(vpb.pipeline_submit(ms, n, vs, origin, op=rec["op"], sdf_out=sdf.numpy(),
+                                            words_out=words.numpy().view(np.uint32)))
+        for (ticket, _keep), rec, (sdf, words) in zip(jobs, recs, outs):
+            vpb.pipeline_wait(ticket)
+            assert f"{oracle.fnv(words.numpy().view(np.uint32)):016x}" == rec["result"]["fnv"]
+            assert f"{oracle.fnv(sdf.numpy()):016x}" == rec["sdf"]["fnv"]
+    # occupancy only
+    rec = golden["bimba_union_bunny_n64"]
+    origin, vs = _frame(oracle, meshes, rec["meshes"], 64)
+    words = np.empty((64 ** 3 + 31) // 32, np.uint32)
+    ticket, _keep = vpb.pipeline_submit([meshes[m] for m in rec["meshes"]], 64, vs, origin, op=rec["op"], words_out=words)
+    vpb.pipeline_wait(ticket)
+    assert f"{oracle.fnv(words):016x}" == rec["result"]["fnv"]
