@@ -510,3 +510,36 @@ def test_pipeline_submit_wait_overlapped_jobs(golden, meshes, oracle, vpb):
     ticket, _keep = vpb.pipeline_submit([meshes[m] for m in rec["meshes"]], 64, vs, origin, op=rec["op"], words_out=words)
     vpb.pipeline_wait(ticket)
     assert f"{oracle.fnv(words):016x}" == rec["result"]["fnv"]
+
+
+def test_config4_10m_faces_surface_and_solid_1024_with_slabs(meshes, oracle, vpb):
+    """BASELINE config 4: the bunny subdivided to 10 785 024 faces, solid + surface voxelization at 1024^3.  Solid and
+    conservative-surface grids equal the oracle bit for bit; the seed-shell surface equals the oracle's shell of the
+    solid; eight z-slabs voxelized separately (the multi-GPU partition: no exchange) concatenate to the one-GPU grid."""
+    import ctypes
+    import torch
+    from cuda_mesh_voxelization_b200 import capi, meshgen
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    v, t = meshgen.bunny_with_faces(*meshes["bunny"], 10785024)
+    assert t.shape[0] == 10785024
+    n = 1024
+    origin, vs = oracle.frame(v, n)
+    solid = vpb.voxelize_host(v, t, n, vs, origin)
+    want = oracle.voxelize(v, t, n, vs, origin)
+    assert np.array_equal(solid, want)
+    assert np.array_equal(vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE), oracle.seed_shell(want, n))
+    assert np.array_equal(vpb.voxelize_host(v, t, n, vs, origin, mode=capi.MODE_SURFACE_CONSERVATIVE),
+                          oracle.voxelize_surface(v, t, n, vs, origin))
+    lib = capi.load()
+    dm = DeviceMesh(v, t, "cuda:0")
+    o = origin.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    T = n // 8
+    full = torch.empty(n ** 3 // 32, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(int(lib.vpb_voxelize_scratch_bytes(n, dm.n_tris, 0, T)), dtype=torch.uint8, device="cuda")
+    for r in range(8):
+        slab = full[r * (n * n * T // 32):(r + 1) * (n * n * T // 32)]
+        capi.check(lib.vpb_voxelize_dev(ctypes.c_void_p(dm.verts.data_ptr()), dm.n_verts, ctypes.c_void_p(dm.tris.data_ptr()),
+                                        dm.n_tris, n, float(vs), o, r * T, (r + 1) * T, ctypes.c_void_p(slab.data_ptr()),
+                                        ctypes.c_void_p(scratch.data_ptr()), scratch.numel(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(full.cpu().numpy().view(np.uint32), want)
