@@ -467,25 +467,67 @@ class SlabPipeline:
     def sdf_host(self):
         return self.sdf.cpu().numpy()
 
-    def run_host(self, host_meshes, op=0, sdf_out=None, words_out=None):
+    def run_host(self, host_meshes, op=0, sdf_out=None, words_out=None, overlap=False):
         """The reference-facing call of a rank (host buffers in, host buffers out): upload the meshes, run the slab
         pipeline, download this rank's slab of the signed distance field (and of the occupancy words) — what
         VOX/CSG/JFA::Compute do with HostVoxelsGrid / HostGrid containers (apps/cli/main.cpp:99-218), with every rank
         moving its own slab over its own PCIe link.  `host_meshes` = [(verts f32 [V,3], tris int32-viewed [T,3])] as
         (pinned) torch tensors; `sdf_out` / `words_out` = (pinned) torch tensors of slab size.  Stream-ordered; the
-        caller synchronises."""
+        caller synchronises.
+        overlap=True: the downloads go to a copy stream from one of two alternating device sdf buffers, so that the next
+        call's kernels run while this call's sdf is still on its way to the host (the host API is PCIe-bound); call
+        finish_host() (or synchronise the device) before reading the outputs, and give consecutive calls different
+        output tensors."""
         torch = self.torch
         from .device import DeviceMesh
         if getattr(self, "_dmesh", None) is None or len(self._dmesh) != len(host_meshes):
             self._dmesh = [DeviceMesh.empty(v.shape[0], t.shape[0], self.device) for v, t in host_meshes]
+        overlap = overlap and not self.alias_sdf
+        main = torch.cuda.current_stream()
+        if overlap:
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._sdf_bufs = [self.sdf, torch.empty_like(self.sdf)]
+                self._sdf_done = [None, None]
+                self._words_done = None
+                self._host_calls = 0
+            b = self._host_calls % 2
+            self._host_calls += 1
+            self.sdf = self._sdf_bufs[b]
+            if self._words_done is not None:
+                main.wait_event(self._words_done)         # the previous call's occupancy has left grid_slab
+            if self._sdf_done[b] is not None:
+                main.wait_event(self._sdf_done[b])        # the call before last has left this sdf buffer
         for dm, (v, t) in zip(self._dmesh, host_meshes):
             dm.verts.copy_(v, non_blocking=True)
             dm.tris.copy_(t, non_blocking=True)
         self.run(self._dmesh, op=op, sdf=sdf_out is not None)
-        if sdf_out is not None:
-            sdf_out.copy_(self.sdf, non_blocking=True)
-        if words_out is not None:
-            words_out.copy_(self.grid_slab, non_blocking=True)
+        if not overlap:
+            if sdf_out is not None:
+                sdf_out.copy_(self.sdf, non_blocking=True)
+            if words_out is not None:
+                words_out.copy_(self.grid_slab, non_blocking=True)
+            return
+        ready = torch.cuda.Event()
+        ready.record(main)
+        cs = self._copy_stream
+        cs.wait_event(ready)
+        with torch.cuda.stream(cs):
+            if words_out is not None:
+                words_out.copy_(self.grid_slab, non_blocking=True)
+            self._words_done = torch.cuda.Event()
+            self._words_done.record(cs)
+            if sdf_out is not None:
+                sdf_out.copy_(self.sdf, non_blocking=True)
+            self._sdf_done[b] = torch.cuda.Event()
+            self._sdf_done[b].record(cs)
+
+    def finish_host(self):
+        """The current stream waits for every download started by run_host(overlap=True)."""
+        main = self.torch.cuda.current_stream()
+        for ev in getattr(self, "_sdf_done", [None, None]):
+            if ev is not None:
+                main.wait_event(ev)
 
 
 class LocalComm:

@@ -417,6 +417,16 @@ def test_slab_pipeline_run_host_matches_reference_digest(golden, meshes, oracle,
         torch.cuda.synchronize()
         assert f"{oracle.fnv(words.numpy().view(np.uint32)):016x}" == rec["result"]["fnv"]
         assert f"{oracle.fnv(sdf.numpy()):016x}" == rec["sdf"]["fnv"]
+    # overlapped form: three calls back to back into alternating outputs (downloads on a copy stream, two device sdf buffers)
+    outs = [(torch.empty_like(sdf).pin_memory(), torch.empty_like(words).pin_memory()) for _ in range(3)]
+    for so, wo in outs:
+        so.fill_(7.0)
+        pipe.run_host(host, op=rec["op"], sdf_out=so, words_out=wo, overlap=True)
+    pipe.finish_host()
+    torch.cuda.synchronize()
+    for so, wo in outs:
+        assert f"{oracle.fnv(wo.numpy().view(np.uint32)):016x}" == rec["result"]["fnv"]
+        assert f"{oracle.fnv(so.numpy()):016x}" == rec["sdf"]["fnv"]
 
 
 # ---------------------------------------------------------------------------------------------- conservative surface mode
