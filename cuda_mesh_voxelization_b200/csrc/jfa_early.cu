@@ -76,10 +76,20 @@ __device__ __forceinline__ void ld4(const uint64_t* p, uint64_t (&v)[4]) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+// point-index offset of the lattice neighbour with scan index k = (dz+1)*9 + (dy+1)*3 + (dx+1), without divisions:
+// k / 9 and k / 3 via multiply-shift (exact for k < 27)
+template <int G>
+__device__ __forceinline__ int c_off27(uint32_t k) {
+    const uint32_t k9 = (k * 57u) >> 9;              // k / 9
+    const uint32_t k3 = (k * 11u) >> 5;              // k / 3
+    const int dz = (int)k9 - 1, dy = (int)(k3 - 3u * k9) - 1, dx = (int)(k - 3u * k3) - 1;
+    return dx * G + dy * (L * G) + dz * (L * L * G);
+}
+
 // G = x-adjacent lattices per CTA.  Point index p = ((l * 8 + j) * 8 + i) * G + g  <->  voxel
 // (rx0 + g + i K, ry + j K, rz + l K).
 template <int G, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 5 * 256 / THREADS)   // 5 CTAs of 256 threads per SM: what 40 KB of lattices per CTA allows
 jfa_early(const EarlyArgs a) {
     constexpr int NP = PTS * G;                    // points per CTA
     constexpr int QUADS = NP / 4;
@@ -176,19 +186,28 @@ jfa_early(const EarlyArgs a) {
                 Y[d] = sqdiff(sy, __ldg(lut + MAXN + (yo[d] ? y + (d - 1) * kk : y)));
                 Z[d] = sqdiff(sz, __ldg(lut + 2 * MAXN + (zo[d] ? z + (d - 1) * kk : z)));
             }
+            // d == 0 can only happen for the source's own voxel: a held seed sits 0, 2, 4 or 6 lattice steps away per axis
+            // (it travelled by 4 and/or 2 so far), a neighbour target is S = 4, 2 or 1 steps away, and positions are
+            // strictly increasing per axis (early_keys_ok) -- so the 26 neighbour keys need no zero test.
+            float XY[3][3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa) XY[b][aa] = __fadd_rn(X[aa], Y[b]);                // (dx*dx)+(dy*dy)
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
 #pragma unroll
                     for (int aa = 0; aa < 3; ++aa) {
-                        if (!(zo[c] && yo[b] && xo[aa])) continue;
                         // the target sees this source at offset (-(aa-1), -(b-1), -(c-1)): scan position of that offset
-                        const uint32_t code = (aa == 1 && b == 1 && c == 1) ? 0u : 1u + (uint32_t)((2 - c) * 9 + (2 - b) * 3 + (2 - aa));
-                        const float d = __fadd_rn(__fadd_rn(X[aa], Y[b]), Z[c]);      // ((dx*dx)+(dy*dy)) + (dz*dz)
-                        const uint32_t kv = d == 0.0f ? code : (((__float_as_uint(d) - a.key_base) << 5) | code);
+                        const bool self = aa == 1 && b == 1 && c == 1;
+                        const uint32_t code = self ? 0u : 1u + (uint32_t)((2 - c) * 9 + (2 - b) * 3 + (2 - aa));
+                        const float d = __fadd_rn(XY[b][aa], Z[c]);                               // ... + (dz*dz)
+                        uint32_t kv = ((__float_as_uint(d) - a.key_base) << 5) | code;
+                        if (self) kv = d == 0.0f ? code : kv;
                         const int t = p + ((aa - 1) * G + (b - 1) * (L * G) + (c - 1) * (L * L * G)) * S;
-                        atomicMin(key + t, kv);
+                        if (zo[c] && yo[b] && xo[aa]) atomicMin(key + t, kv);                     // predicated, no branch
                     }
                 }
         }
@@ -211,9 +230,8 @@ jfa_early(const EarlyArgs a) {
                 held |= 1u << (4 * m + u);
                 const uint32_t code = kq[u] & 31u;
                 if (code == 0u) continue;
-                const int idx = (int)code - 1;             // (dz+1)*9 + (dy+1)*3 + (dx+1)
-                const int dz = idx / 9 - 1, dy = (idx / 3) % 3 - 1, dx = idx % 3 - 1;
-                fresh[m][u] = st[p + u + (dx * G + dy * (L * G) + dz * (L * L * G)) * S];
+                // code - 1 = (dz+1)*9 + (dy+1)*3 + (dx+1)  ->  point offset of that neighbour at stride 1
+                fresh[m][u] = st[p + u + c_off27<G>(code - 1u) * S];
                 moved |= 1u << (4 * m + u);
             }
         }
@@ -244,7 +262,10 @@ jfa_early(const EarlyArgs a) {
         ld4(st + p, v);
         if (a.T) {
             const uint32_t owner = z / a.T;
-            st4(a.dst_rank[owner] + ((size_t)(z - owner * a.T) * n + y) * n + x, v);    // 7 of 8 planes: a store over NVLink
+            state_t* base = a.dst_rank[0];             // selects, not an indexed read: no local copy of the parameter array
+#pragma unroll
+            for (uint32_t r = 1; r < 8; ++r) base = owner == r ? a.dst_rank[r] : base;
+            st4(base + ((size_t)(z - owner * a.T) * n + y) * n + x, v);                  // 7 of 8 planes: a store over NVLink
         } else {
             st4(a.dst + ((size_t)(z - a.z0) * n + y) * n + x, v);
         }
