@@ -100,6 +100,8 @@ jfa_early(const EarlyArgs a) {
     uint32_t* const key = reinterpret_cast<uint32_t*>(st + NP);          // [NP] best key of the running pass
     uint16_t* const list = reinterpret_cast<uint16_t*>(key + NP);        // [NP] points that hold a seed
     __shared__ int s_count;
+    __shared__ int s_off27[27];
+    if (threadIdx.x < 27) s_off27[threadIdx.x] = c_off27<G>(threadIdx.x);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = a.n, K = a.K;
@@ -230,8 +232,9 @@ jfa_early(const EarlyArgs a) {
                 held |= 1u << (4 * m + u);
                 const uint32_t code = kq[u] & 31u;
                 if (code == 0u) continue;
-                // code - 1 = (dz+1)*9 + (dy+1)*3 + (dx+1)  ->  point offset of that neighbour at stride 1
-                fresh[m][u] = st[p + u + c_off27<G>(code - 1u) * S];
+                // code - 1 = (dz+1)*9 + (dy+1)*3 + (dx+1)  ->  point offset of that neighbour at stride 1 (table: the
+                // division chain was 16 % of the kernel's instructions, profiles/r01_v11_flood_summary.txt)
+                fresh[m][u] = st[p + u + s_off27[code - 1u] * S];
                 moved |= 1u << (4 * m + u);
             }
         }

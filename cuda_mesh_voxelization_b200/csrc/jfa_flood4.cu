@@ -258,6 +258,18 @@ struct Flood4 {
             constexpr bool T0 = M != M_LAST, T1 = M == M_ALL, T2 = M != M_FIRST;   // which targets this plane feeds
             constexpr bool TT[3] = {T0, T1, T2};
             const bool in_grid = plane_in_grid(p);
+            // FINAL: the occupancy bits of output plane p-1 (its sign) are requested before the candidate arithmetic, not
+            // right before the store (that dependent load was 18 % of the final pass's stall samples,
+            // profiles/r01_v11_hot_lines.txt)
+            uint32_t wpre[2] = {0u, 0u};
+            if (FINAL && T2 && p >= 1) {
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    if (!ok[r2]) continue;
+                    const size_t bit = ((size_t)(zl0 + (p - 1) * k + (int)a.z0) * n + (gy0 + r2 * k)) * n + x0;
+                    wpre[r2] = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
+                }
+            }
             if (ok[0] && in_grid) {
                 const float* fb = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW + tbase;
                 const uint32_t tag = (uint32_t)(((p + 1) & 3) * C::PW);
@@ -382,8 +394,7 @@ struct Flood4 {
                     if (!FINAL) {
                         st_pair(a.dst + vox, s2[0], s2[1]);
                     } else {
-                        const size_t bit = ((size_t)(zl + a.z0) * n + gy) * n + x0;
-                        const uint32_t w = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
+                        const uint32_t w = wpre[r2];
                         *reinterpret_cast<float2*>(a.sdf + vox) = make_float2((w & 1u) ? d2[0] : -d2[0], (w & 2u) ? d2[1] : -d2[1]);
                         if (a.seeds) *reinterpret_cast<uint2*>(a.seeds + vox) = make_uint2(jfa_public(s2[0]), jfa_public(s2[1]));
                     }
