@@ -73,11 +73,12 @@ template <int SS, int TR>
 struct Cfg {
     static constexpr int NW = TR / 2;                 // warps per CTA: one per pair of lattice rows
     static constexpr int THREADS = NW * 32;
-    static constexpr int W = SEG + 2 * SS;            // staged window per row (SS = 64: three 64-wide segments)
+    static constexpr int XL = SS == 1 ? 2 : SS;       // entries staged left of the segment (SS = 1: two, so that pairs stay aligned)
+    static constexpr int W = SEG + 2 * XL;            // staged window per row (SS = 64: three 64-wide segments)
     static constexpr int ROWS = TR + 2;
     static constexpr int PW = ROWS * W;               // entries per staged plane
-    static constexpr bool ALIGNED = (SS % 2) == 0;    // staged/evaluated in aligned pairs
-    static constexpr int G = ALIGNED ? 2 : 1;         // entries per staging item
+    static constexpr bool ALIGNED = true;             // staged in aligned pairs (every stride: the SS = 1 window starts at xs - 2)
+    static constexpr int G = 2;                       // entries per staging item
     static constexpr int ITEMS = PW / G;
     static constexpr int NP = (ITEMS + THREADS - 1) / THREADS;
     static constexpr int NBUF = SS >= 64 ? 1 : 2;     // float planes double-buffered unless the window is 192 wide
@@ -116,18 +117,19 @@ struct Flood4 {
     using C = Cfg<SS, TR>;
 
     static __device__ __forceinline__ int gx_of(int i, int xs, int k) {
-        return (SS < 64) ? (xs - SS + i) : (xs + (i / SEG - 1) * k + (i % SEG));
+        return (SS < 64) ? (xs - C::XL + i) : (xs + (i / SEG - 1) * k + (i % SEG));
     }
 
     // the three candidate columns of one staged row, for the thread's two x-adjacent voxels
     static __device__ __forceinline__ void load_row(const float* p, float2 (&o)[3]) {
-        if (C::ALIGNED) {
+        if (SS > 1) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) o[c] = *reinterpret_cast<const float2*>(p + c * SS);
-        } else {   // SS == 1: entries x0-1 .. x0+2
+        } else {   // SS == 1: the window starts at x0 - 2; columns x0-1 | x0 | x0+1 for the first voxel, +1 for the second
             const float2 a = *reinterpret_cast<const float2*>(p);
             const float2 b = *reinterpret_cast<const float2*>(p + 2);
-            o[0] = a; o[1] = make_float2(a.y, b.x); o[2] = b;
+            const float2 c = *reinterpret_cast<const float2*>(p + 4);
+            o[0] = make_float2(a.y, b.x); o[1] = b; o[2] = make_float2(b.y, c.x);
         }
     }
 
@@ -383,7 +385,9 @@ struct Flood4 {
                     for (int v = 0; v < 2; ++v) {
                         const uint32_t key = accP.key[r2][v];
                         const uint32_t code = key & 15u;
-                        const uint32_t e = accP.tag[r2][v] + (uint32_t)(tbase + r2 * C::W + v) + (code >> 2) * C::W + (code & 3u) * SS;
+                        // ring entry of candidate (row code >> 2, column code & 3) of voxel v (SS = 1: column c of voxel v sits
+                        // at window index 2*lane + 1 + c + v)
+                        const uint32_t e = accP.tag[r2][v] + (uint32_t)(tbase + r2 * C::W + v + (SS == 1 ? 1 : 0)) + (code >> 2) * C::W + (code & 3u) * SS;
                         s2[v] = ring[e];
                         if (FINAL) {
                             const float d = (key >> 4) ? __uint_as_float((key >> 4) + a.key_base) : 0.0f;
