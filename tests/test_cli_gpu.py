@@ -64,3 +64,24 @@ def test_cli_rejects_other_backends(cli, tmp_path, meshes):
     write_obj(p, *meshes["d20"])
     out = subprocess.run([cli, str(p), "-n", "32", "-t", "0"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "B200 back-end" in out.stderr
+
+
+def test_benchmarks_runner_writes_reference_layout_csvs(cli, tmp_path, meshes):
+    """tools/benchmarks.py (the reference's scripts/benchmarks.py command line and CSV layout) over our CLI:
+    one CSV per (mesh, main label), one row per iteration and size, total + ::memory / ::processing columns."""
+    import csv
+    import sys
+    folder = tmp_path / "meshes"
+    folder.mkdir()
+    write_obj(folder / "d20.obj", *meshes["d20"])
+    (tmp_path / "out").mkdir()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "benchmarks.py"), "--niter", "2", "--folder", str(folder),
+                          "--minsize", "32", "--maxsize", "64", "--output", str(tmp_path / "bench"), "--exec", cli],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    vox = list(csv.reader(open(tmp_path / "bench" / "d20" / "d20_b200_vox.csv")))
+    assert vox[0] == ["size", "b200_vox", "b200_vox__memory", "b200_vox__processing"]
+    assert [r[0] for r in vox[1:]] == ["32", "32", "64", "64"]
+    assert all(float(x) >= 0 for r in vox[1:] for x in r[1:])
+    jfa = list(csv.reader(open(tmp_path / "bench" / "d20" / "d20_b200_jfa.csv")))
+    assert jfa[0][:2] == ["size", "b200_jfa"] and len(jfa) == 5
