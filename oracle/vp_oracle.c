@@ -13,6 +13,10 @@
  * (oracle/_ref/libvpref.so) in the build container, and (when oracle/_ref exists) against the live
  * reference on the same inputs.
  *
+ * ONE EXCEPTION, PARITY UNPINNED: vpo_voxelize_surface (conservative Schwarz-Seidel surface voxelization) restates no
+ * reference code -- the reference has no surface voxelizer -- and is pinned only against an independent float64
+ * separating-axis test (tests/test_oracle_golden.py).
+ *
  * Behaviour where the reference is undefined (never reached by closed meshes inside their own
  * bounding box; counted in `stats` so tests can assert that):
  *   - a (y,z) cell outside the grid              -> skipped      (reference: out-of-bounds / aliased write)
