@@ -45,6 +45,11 @@ namespace {
 #endif
 
 constexpr int SEG = 64;          // voxels in x per warp (2 per lane)
+#ifdef VPB_STATE64
+typedef size_t vox_t;            // element offset inside a slab / bit index inside the grid
+#else
+typedef uint32_t vox_t;          // N <= 1024: both are below 2^30, 32-bit index arithmetic is exact
+#endif
 constexpr int MAXN = JFA_MAXN;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t OWN_CODE = 5;   // (dy,dx) code of the centre: row 1, column 1
@@ -143,6 +148,9 @@ struct Flood4 {
         extern __shared__ __align__(16) float sm[];
         const int n = (int)a.n, k = a.k;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // ring-entry offset of the candidate with in-plane code r*4 + c (row r, column c): r * W + c * SS
+        __shared__ uint32_t s_dec[16];
+        if (threadIdx.x < 16) s_dec[threadIdx.x] = (threadIdx.x >> 2) * (uint32_t)C::W + (threadIdx.x & 3u) * (uint32_t)SS;
         float* const lut = sm;                                     // px | py | pz
         float* const fbuf = sm + 3 * MAXN;                         // NBUF x (fx | fy | fz) planes
         state_t* const ring = reinterpret_cast<state_t*>(fbuf + C::NBUF * 3 * C::PW);     // 4 packed planes
@@ -268,7 +276,7 @@ struct Flood4 {
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
                     if (!ok[r2]) continue;
-                    const size_t bit = ((size_t)(zl0 + (p - 1) * k + (int)a.z0) * n + (gy0 + r2 * k)) * n + x0;
+                    const vox_t bit = ((vox_t)(zl0 + (p - 1) * k + (int)a.z0) * n + (gy0 + r2 * k)) * n + x0;
                     wpre[r2] = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
                 }
             }
@@ -387,14 +395,14 @@ struct Flood4 {
                         const uint32_t code = key & 15u;
                         // ring entry of candidate (row code >> 2, column code & 3) of voxel v (SS = 1: column c of voxel v sits
                         // at window index 2*lane + 1 + c + v)
-                        const uint32_t e = accP.tag[r2][v] + (uint32_t)(tbase + r2 * C::W + v + (SS == 1 ? 1 : 0)) + (code >> 2) * C::W + (code & 3u) * SS;
+                        const uint32_t e = accP.tag[r2][v] + (uint32_t)(tbase + r2 * C::W + v + (SS == 1 ? 1 : 0)) + s_dec[code];
                         s2[v] = ring[e];
                         if (FINAL) {
                             const float d = (key >> 4) ? __uint_as_float((key >> 4) + a.key_base) : 0.0f;
                             d2[v] = s2[v] ? d : INFINITY;
                         }
                     }
-                    const size_t vox = ((size_t)zl * n + gy) * n + x0;
+                    const vox_t vox = ((vox_t)zl * n + gy) * n + x0;
                     if (!FINAL) {
                         st_pair(a.dst + vox, s2[0], s2[1]);
                     } else {
