@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,7 @@ struct Options {
     int operation = 0;
     bool exportPhases = false, sdf = false, fused = false, help = false;
     unsigned blockSize = 32, iterations = 1;
+    int gpus = 1;
 };
 
 void usage() {
@@ -44,34 +46,72 @@ void usage() {
                 "  -h, --help            Print usage\n");
 }
 
+// cxxopts-compatible subset (the reference vendors cxxopts 3.3.1): `-n 128`, `-n128`, `--num-voxels 128`,
+// `--num-voxels=128`, grouped boolean short flags (`-se`), positional file names.  Anything malformed prints the usage
+// text and exits with 1 instead of throwing.
 bool parse(int argc, char** argv, Options& o) {
-    auto value = [&](int& i, const std::string& a, std::string& out) {
-        const size_t eq = a.find('=');
-        if (eq != std::string::npos) { out = a.substr(eq + 1); return true; }
-        if (a.size() > 2 && a[0] == '-' && a[1] != '-') { out = a.substr(2); return true; }   // -n128
-        if (i + 1 >= argc) return false;
-        out = argv[++i];
+    struct Opt { char s; const char* l; bool flag; };
+    static const Opt table[] = {{'h', "help", true}, {'e', "export", true}, {'s', "sdf", true}, {0, "fused", true},
+                                {'n', "num-voxels", false}, {'t', "type", false}, {'o', "output", false},
+                                {'p', "operation", false}, {'b', "block-size", false}, {'m', "benckmark", false},
+                                {'i', "filenames", false}, {0, "gpus", false}};
+    auto apply = [&](const Opt& d, const std::string& v) -> bool {
+        const std::string name = d.l;
+        try {
+            size_t used = 0;
+            auto num = [&](long lo, long hi) -> long {
+                const long x = std::stol(v, &used, 10);
+                if (used != v.size() || x < lo || x > hi) throw std::invalid_argument(v);
+                return x;
+            };
+            if (name == "help") o.help = true;
+            else if (name == "export") o.exportPhases = true;
+            else if (name == "sdf") o.sdf = true;
+            else if (name == "fused") o.fused = true;
+            else if (name == "num-voxels") o.numVoxels = (unsigned)num(1, 1 << 20);
+            else if (name == "type") o.type = (int)num(0, 64);
+            else if (name == "output") o.output = v;
+            else if (name == "operation") o.operation = (int)num(0, 3);
+            else if (name == "block-size") o.blockSize = (unsigned)num(1, 1 << 20);
+            else if (name == "benckmark") o.iterations = (unsigned)num(1, 1 << 30);
+            else if (name == "filenames") o.filenames.push_back(v);
+            else if (name == "gpus") o.gpus = (int)num(1, 64);
+        } catch (const std::exception&) {
+            std::fprintf(stderr, "option --%s: bad value '%s'\n", d.l, v.c_str());
+            return false;
+        }
         return true;
     };
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
-        std::string v;
-        auto is = [&](const char* s, const char* l) {
-            return a == s || a == l || a.rfind(std::string(l) + "=", 0) == 0 || (a.size() > 2 && a.rfind(s, 0) == 0 && a[1] != '-');
-        };
-        if (a == "-h" || a == "--help") o.help = true;
-        else if (a == "-e" || a == "--export") o.exportPhases = true;
-        else if (a == "-s" || a == "--sdf") o.sdf = true;
-        else if (a == "--fused") o.fused = true;
-        else if (is("-n", "--num-voxels")) { if (!value(i, a, v)) return false; o.numVoxels = (unsigned)std::stoul(v); }
-        else if (is("-t", "--type")) { if (!value(i, a, v)) return false; o.type = std::stoi(v); }
-        else if (is("-o", "--output")) { if (!value(i, a, v)) return false; o.output = v; }
-        else if (is("-p", "--operation")) { if (!value(i, a, v)) return false; o.operation = std::stoi(v); }
-        else if (is("-b", "--block-size")) { if (!value(i, a, v)) return false; o.blockSize = (unsigned)std::stoul(v); }
-        else if (is("-m", "--benckmark")) { if (!value(i, a, v)) return false; o.iterations = (unsigned)std::stoul(v); }
-        else if (is("-i", "--filenames")) { if (!value(i, a, v)) return false; o.filenames.push_back(v); }
-        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
-        else o.filenames.push_back(a);
+        if (a.size() >= 3 && a[0] == '-' && a[1] == '-') {                    // --long, --long=value, --long value
+            const size_t eq = a.find('=');
+            const std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            const Opt* d = nullptr;
+            for (const Opt& t : table) if (name == t.l) d = &t;
+            if (!d) { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
+            if (d->flag) { if (eq != std::string::npos || !apply(*d, "")) return false; continue; }
+            std::string v;
+            if (eq != std::string::npos) v = a.substr(eq + 1);
+            else if (i + 1 < argc) v = argv[++i];
+            else { std::fprintf(stderr, "option %s needs a value\n", a.c_str()); return false; }
+            if (!apply(*d, v)) return false;
+        } else if (a.size() >= 2 && a[0] == '-' && a != "--") {                // -x, -xVALUE, -x VALUE, -abc (flags)
+            for (size_t c = 1; c < a.size(); ++c) {
+                const Opt* d = nullptr;
+                for (const Opt& t : table) if (t.s && a[c] == t.s) d = &t;
+                if (!d) { std::fprintf(stderr, "unknown option -%c\n", a[c]); return false; }
+                if (d->flag) { if (!apply(*d, "")) return false; continue; }
+                std::string v;
+                if (c + 1 < a.size()) v = a.substr(c + 1);
+                else if (i + 1 < argc) v = argv[++i];
+                else { std::fprintf(stderr, "option -%c needs a value\n", a[c]); return false; }
+                if (!apply(*d, v)) return false;
+                break;
+            }
+        } else {
+            o.filenames.push_back(a);
+        }
     }
     return true;
 }
@@ -87,6 +127,9 @@ int main(int argc, char** argv) {
     if (opt.help) { usage(); return 0; }
     cpuAssert(opt.filenames.size() >= 1, "Need [input filename]");
     cpuAssert(opt.blockSize % 16 == 0, "Thread per voxel must be a multiple of 16");
+    // benchmark mode folds grids[0] with an EMPTY grid per iteration (main.cpp:89,126-127,188); the fused call has no such
+    // operand, so the [B200CSG] lines tools/benchmarks.py parses would silently disappear: refuse the combination
+    cpuAssert(!(opt.fused && opt.iterations > 1), "--fused cannot be combined with -m (benchmark mode times the stages one by one)");
     cpuAssert(opt.type == static_cast<int>(Types::B200),
               "this build only contains the B200 back-end: use -t 4 (the reference's -t 0..3 live in the reference build)");
 

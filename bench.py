@@ -114,9 +114,10 @@ def ncu_traffic(n, world):
 
 # ------------------------------------------------------------------------------------------ reference arm
 
-def cpu_pipeline(lib, kind, meshes, n, origin_vs=None, op=1):
-    """One pass of the reference CPU path (-t 3 flavour: sequential voxelization — the only CPU voxelizer the CLI
-    ever calls, apps/cli/main.cpp:99-103 — then OpenMP CSG and JFA with every host thread)."""
+def cpu_pipeline(lib, kind, meshes, n, origin_vs=None, op=1, openmp=True):
+    """One pass of the reference CPU path.  openmp=True is the CLI's -t 3 flavour: sequential voxelization — the only
+    CPU voxelizer the CLI ever calls, apps/cli/main.cpp:99-103 — then OpenMP CSG and JFA with every host thread;
+    openmp=False is -t 0 (csg/sequential.cpp, jfa/sequential.cpp:68-125), one thread."""
     if origin_vs is None:
         origin, vs = lib.frame(np.concatenate([m[0] for m in meshes]), n)
     else:
@@ -124,37 +125,60 @@ def cpu_pipeline(lib, kind, meshes, n, origin_vs=None, op=1):
     t0 = time.perf_counter()
     grids = [lib.voxelize(*m, n, vs, origin) for m in meshes]
     if kind == "reference":
-        acc = lib.csg(grids[0], grids[1], n, op, openmp=True)
-        lib.jfa(acc, n, vs, origin, openmp=True)
+        acc = lib.csg(grids[0], grids[1], n, op, openmp=openmp)
+        lib.jfa(acc, n, vs, origin, openmp=openmp)
     else:
         acc = lib.csg(grids[0], grids[1], n, op)
         lib.jfa(acc, n, vs, origin)
     return time.perf_counter() - t0
 
 
+def host_cores():
+    """Hardware threads this process may run on (what the OpenMP runtime would use by default outside torchrun)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_arm():
+    """The CPU checker to time and the number of threads its OpenMP legs will REALLY use.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers; the reference build's team size is therefore set through the OpenMP API
+    (oracle/ref_probe.cu vpref_set_threads) and read back with omp_get_max_threads(), not guessed from the environment."""
     from checkers import Oracle, Reference
+    want = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(want)       # the oracle port (libgomp reads it at load time) and any child
     if Reference.available():
-        return Reference(), "reference"
-    return Oracle(), "port"
+        lib = Reference()
+        got = lib.set_threads(want)
+        if got != want:
+            raise SystemExit(f"bench.py: the reference's OpenMP runtime reports {got} threads, asked for {want}")
+        return lib, "reference", got
+    return Oracle(), "port", want
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lib, kind = cpu_arm()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    lib, kind, cores = cpu_arm()
     n_s = args.ref_n
     meshes, _, _ = load_workload(n_s, args.faces)
-    for _ in range(args.warmup):
+    # the largest sample that fits the time box: 512^3 per step unless the first step says (W + K) of them take > 5 min
+    t_first = cpu_pipeline(lib, kind, meshes, n_s, op=OPS[args.op][0])
+    done_warm = 1
+    if n_s > 256 and t_first * (args.warmup + args.steps) > 300.0:
+        log(f"reference arm: one {n_s}^3 step took {t_first:.1f} s; sampling at 256^3 to stay inside the time box")
+        n_s = 256
+        meshes, _, _ = load_workload(n_s, args.faces)
+        done_warm = 0
+    for _ in range(max(0, args.warmup - done_warm)):
         cpu_pipeline(lib, kind, meshes, n_s, op=OPS[args.op][0])
     t = [cpu_pipeline(lib, kind, meshes, n_s, op=OPS[args.op][0]) for _ in range(args.steps)]
     total = sum(t)
     value = n_s ** 3 * args.steps / total / 1e9
     sample = (f"{n_s}^3 grid per step (the workload's meshes and stages at 1/{(args.n // n_s) ** 3} of its voxels): "
-              f"sequential voxelization + OpenMP CSG + OpenMP JFA, {cores} threads")
+              f"sequential voxelization + OpenMP CSG + OpenMP JFA (-t 3), {cores} OpenMP threads (omp_get_max_threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -173,6 +197,26 @@ OPS = {"union": (1, "∪"), "intersection": (2, "∩"), "difference": (3, "−")
 def workload_name(args):
     return (f"bunny subdivided to {args.faces} faces {OPS[args.op][1]} bimba (46220 faces), solid voxelization + CSG "
             f"{args.op} + JFA SDF at {args.n}^3")
+
+
+def golden_parity(args, digest):
+    """Compares the run's sdf digests with the reference-generated ones (tests/golden/ref_digests_large.json, made by
+    tests/golden/make_golden_large.py from the unmodified reference's OpenMP JFA).  "green" = every z-chunk of the final
+    sdf (and, on one GPU, the whole sdf and the occupancy) is byte-identical to the reference's."""
+    if not digest:
+        return {"status": "unchecked", "why": "no host copy of the sdf in this run"}
+    name = {(1024, 1348128, "union"): "bunny1348128_union_bimba_n1024"}.get((args.n, args.faces, args.op))
+    p = os.path.join(ROOT, "tests", "golden", "ref_digests_large.json")
+    if not name or not os.path.exists(p):
+        return {"status": "unchecked", "why": "no reference digest for this configuration"}
+    rec = json.load(open(p)).get(name)
+    if not rec:
+        return {"status": "unchecked", "why": f"{name} missing from ref_digests_large.json"}
+    ok = digest.get("sdf_fnv_z8") == rec["sdf"]["fnv_z8"]
+    if "sdf_fnv" in digest:
+        ok = ok and digest["sdf_fnv"] == rec["sdf"]["fnv"] and digest["words_fnv"] == rec["result"]["fnv"]
+    return {"status": "green" if ok else "MISMATCH", "against": f"tests/golden/ref_digests_large.json:{name} "
+            "(reference jfa/openmp.cpp on the same meshes)"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -277,6 +321,7 @@ def run_ours(args):
 
     # ---- end to end through the reference-facing C-ABI call, host buffers, copies inside the timed region
     e2e = None
+    digest = None
     if world == 1 and n <= 1024:   # above 1024^3 the host-side SDF alone is 32 GiB of pinned memory: device-resident only
         pv = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v, _ in meshes]
         pt = [torch.from_numpy(np.ascontiguousarray(t).view(np.int32)).pin_memory() for _, t in meshes]
@@ -317,6 +362,9 @@ def run_ours(args):
         t0 = time.perf_counter()
         pipelined(args.steps)
         dt = time.perf_counter() - t0
+        last_sdf, last_words = outs[(args.steps - 1) % 2]
+        digest = {"sdf_fnv_z8": capi.fnv_chunks(last_sdf, 8), "sdf_fnv": capi.fnv_chunks(last_sdf, 1)[0],
+                  "words_fnv": capi.fnv_chunks(last_words, 1)[0], "of": "the last e2e step's host buffers"}
         e2e = {"value": n ** 3 * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / args.steps * 1e3,
                "api": "vpb_pipeline_submit / vpb_pipeline_wait (pinned host buffers, two jobs in flight: step i+1's kernels "
@@ -346,6 +394,12 @@ def run_ours(args):
         t = torch.tensor([a0.elapsed_time(a1)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item()) * 1e-3
+        # FNV-1a-64 of every N/8-plane z-chunk of the sdf, from the last step's host slabs: the list is the same for
+        # every GPU count and is compared with the reference's golden digests below
+        mine = capi.fnv_chunks(outs[(args.steps - 1) % 2][0].numpy(), 8 // world) if 8 % world == 0 else []
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        digest = {"sdf_fnv_z8": [h for part in parts for h in part], "of": "the last e2e step's host slabs, rank by rank"}
         h2d = sum(v.numel() * 4 + t_.numel() * 4 for v, t_ in host_meshes) * world
         d2h = n ** 3 * 4 + capi.n_words(n) * 4
         e2e = {"value": n ** 3 * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -361,16 +415,22 @@ def run_ours(args):
     # ---- CPU baseline beside it: the reference's own CPU path on a bounded sample (N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        lib, kind = cpu_arm()
-        cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        lib, kind, cores = cpu_arm()
         n_s = args.ref_n
         ms_, _, _ = load_workload(n_s, args.faces)
         dt = cpu_pipeline(lib, kind, ms_, n_s, op=OPS[args.op][0])
         cpu = {"value": n_s ** 3 / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"one step at {n_s}^3 (same meshes and stages, 1/{(n // n_s) ** 3} of the voxels): sequential "
-                         f"voxelization + OpenMP CSG + OpenMP JFA, {dt:.2f} s"}
+                         f"voxelization + OpenMP CSG + OpenMP JFA (-t 3), {cores} OpenMP threads, {dt:.2f} s"}
+        # the reference's sequential path (-t 0: csg/sequential.cpp, jfa/sequential.cpp) beside it, one thread
+        n_q = args.seq_n
+        if n_q:
+            mq, _, _ = load_workload(n_q, args.faces)
+            dq = cpu_pipeline(lib, kind, mq, n_q, op=OPS[args.op][0], openmp=False)
+            cpu["sequential"] = {"value": n_q ** 3 / dq / 1e9, "unit": UNIT, "cores": 1,
+                                 "sample": f"one step at {n_q}^3, -t 0 (sequential voxelization, CSG and JFA), {dq:.2f} s"}
 
+    parity = golden_parity(args, digest)
     value = n ** 3 * args.steps / (ms_total * 1e-3) / 1e9
     transport = partition_label
     line = {
@@ -389,6 +449,7 @@ def run_ours(args):
                      "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes,
                      "ms_per_launch": mean_pass_ms, "ms_early_seed_plus_3_passes": early_ms, "ms_per_pass_by_k": {str(k): v for k, v in sorted(pass_avg.items(), reverse=True)}},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "digest": digest, "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -405,12 +466,14 @@ def main():
     ap.add_argument("--faces", type=int, default=1348128)
     ap.add_argument("--op", default="union", choices=sorted(OPS), help="CSG operator folding bimba into the bunny")
     ap.add_argument("--ref-n", type=int, default=0,
-                    help="grid side of the bounded CPU sample (default: 512 for the cpu_baseline of our arm = ~20-30 s of CPU "
-                         "work once, 256 per step for --impl reference)")
+                    help="grid side of the bounded CPU sample (default 512: ~20 s of CPU work per step on 32 cores; the "
+                         "reference arm drops to 256 by itself when W + K such steps would not fit 5 minutes)")
+    ap.add_argument("--seq-n", type=int, default=256, help="grid side of the one -t 0 (sequential) CPU step timed beside "
+                    "the OpenMP one in cpu_baseline (0 = skip; 256^3 is ~15-20 s on one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if not args.ref_n:
-        args.ref_n = 256 if args.impl == "reference" else 512
+        args.ref_n = 512
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -25,6 +25,7 @@ SIGNATURES = [
     ("vpb_device_count", ctypes.c_int, []),
     ("vpb_kernel_launches", ctypes.c_uint64, []),
     ("vpb_last_timing", ctypes.c_int, [_f32p]),
+    ("vpb_fnv1a64_chunks", ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, _u64p]),
     ("vpb_voxelize_host", ctypes.c_int, [_f32p, ctypes.c_uint64, _u32p, ctypes.c_uint64, ctypes.c_uint32,
                                          ctypes.c_float, _f32p, ctypes.c_int, _u32p]),
     ("vpb_csg_host", ctypes.c_int, [_u32p, _u32p, ctypes.c_uint32, ctypes.c_int]),
@@ -121,6 +122,14 @@ def last_timing():
     t = np.zeros(3, np.float32)
     check(load().vpb_last_timing(_fp(t)))
     return {"h2d_ms": float(t[0]), "kernels_ms": float(t[1]), "d2h_ms": float(t[2])}
+
+
+def fnv_chunks(arr, chunks: int = 1):
+    """FNV-1a-64 of `chunks` equal consecutive pieces of a host array (hex strings); chunks=1 is the reference digest."""
+    arr = np.ascontiguousarray(arr)
+    out = np.zeros(chunks, np.uint64)
+    check(load().vpb_fnv1a64_chunks(arr.ctypes.data, arr.nbytes, chunks, out.ctypes.data_as(_u64p)))
+    return [f"{int(h):016x}" for h in out]
 
 
 def kernel_launches() -> int:

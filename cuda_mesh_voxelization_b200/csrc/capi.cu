@@ -4,10 +4,13 @@
 // e.g. vox/naive.cu:91-121, jfa/tiled.cu:250-336) with one stream, grow-only device buffers that survive
 // between calls, and stage-to-stage device residency inside vpb_pipeline_host.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -16,7 +19,8 @@ namespace vpb {
 namespace {
 
 thread_local char g_err[512] = "";
-uint64_t g_launches = 0;
+std::atomic<uint64_t> g_launches{0};
+std::mutex g_api_mutex;          // vpb_init / vpb_shutdown; the compute entry points keep vplib's one-caller-thread rule
 
 struct Buf {
     void* p = nullptr;
@@ -190,7 +194,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
 }
-void count_launch(unsigned n) { g_launches += n; }
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int num_sms() { return g_ctx.sms; }
 
 }  // namespace vpb
@@ -208,9 +212,45 @@ int vpb_device_count(void) {
     return n;
 }
 
+static int create_resources() {
+    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : g_ctx.ev) VPB_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : g_ctx.chunk_ev) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    VPB_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_done, cudaEventDisableTiming));
+    for (auto& ev : g_ctx.slot_done) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return VPB_OK;
+}
+
+// frees whatever exists (also the partially built context of a failed vpb_init)
+static void release_resources() {
+    if (g_ctx.stream) cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
+    for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.scratch, &g_ctx.state_a,
+                   &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds, &g_ctx.slot_words[0], &g_ctx.slot_words[1], &g_ctx.slot_sdf[0],
+                   &g_ctx.slot_sdf[1]})
+        b->release();
+    jfa_lut_release();
+    jfa_lut_release_s64();
+    for (auto& ev : g_ctx.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : g_ctx.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : g_ctx.slot_done) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    if (g_ctx.copy_done) cudaEventDestroy(g_ctx.copy_done);
+    g_ctx.copy_done = nullptr;
+    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
+    g_ctx.copy_stream = nullptr;
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+}
+
 int vpb_init(int device) {
+    std::lock_guard<std::mutex> guard(g_api_mutex);
     if (g_ctx.ready && g_ctx.device == device) return VPB_OK;
-    if (g_ctx.ready) vpb_shutdown();
+    if (g_ctx.ready) {
+        cudaSetDevice(g_ctx.device);
+        release_resources();
+        g_ctx.ready = false;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -228,12 +268,11 @@ int vpb_init(int device) {
     }
     g_ctx.sms = prop.multiProcessorCount;
     g_ctx.device = device;
-    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-    for (auto& ev : g_ctx.ev) VPB_CUDA(cudaEventCreate(&ev));
-    for (auto& ev : g_ctx.chunk_ev) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    VPB_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_done, cudaEventDisableTiming));
-    for (auto& ev : g_ctx.slot_done) VPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const int rc = create_resources();
+    if (rc != VPB_OK) {
+        release_resources();
+        return rc;
+    }
     g_ctx.slot_ticket[0] = g_ctx.slot_ticket[1] = 0;
     g_ctx.next_ticket = 1;
     g_ctx.ready = true;
@@ -242,33 +281,42 @@ int vpb_init(int device) {
 }
 
 void vpb_shutdown(void) {
+    std::lock_guard<std::mutex> guard(g_api_mutex);
     if (!g_ctx.ready) return;
     cudaSetDevice(g_ctx.device);
-    cudaStreamSynchronize(g_ctx.stream);
-    if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
-    for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.scratch, &g_ctx.state_a,
-                   &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds})
-        b->release();
-    for (auto& ev : g_ctx.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-    for (auto& ev : g_ctx.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-    for (auto& ev : g_ctx.slot_done) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-    for (Buf* b : {&g_ctx.slot_words[0], &g_ctx.slot_words[1], &g_ctx.slot_sdf[0], &g_ctx.slot_sdf[1]}) b->release();
-    if (g_ctx.copy_done) cudaEventDestroy(g_ctx.copy_done);
-    g_ctx.copy_done = nullptr;
-    cudaStreamSynchronize(g_ctx.copy_stream);
-    cudaStreamDestroy(g_ctx.copy_stream);
-    g_ctx.copy_stream = nullptr;
-    cudaStreamDestroy(g_ctx.stream);
-    g_ctx.stream = nullptr;
+    release_resources();
     g_ctx.ready = false;
 }
 
 const char* vpb_last_error(void) { return g_err; }
-uint64_t vpb_kernel_launches(void) { return g_launches; }
+uint64_t vpb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int vpb_last_timing(float out[3]) {
     VPB_REQUIRE(out, "vpb_last_timing: null");
     memcpy(out, g_ctx.timing, sizeof g_ctx.timing);
+    return VPB_OK;
+}
+
+int vpb_fnv1a64_chunks(const void* data, uint64_t bytes, uint32_t chunks, uint64_t* out) {
+    VPB_REQUIRE(out && chunks >= 1 && chunks <= 4096 && (data || bytes == 0), "fnv1a64_chunks: bad argument");
+    VPB_REQUIRE(bytes % chunks == 0, "fnv1a64_chunks: %llu bytes do not split into %u equal chunks", (unsigned long long)bytes, chunks);
+    const uint64_t per = bytes / chunks;
+    auto one = [=](uint32_t c) {
+        const unsigned char* p = static_cast<const unsigned char*>(data) + (uint64_t)c * per;
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t i = 0; i < per; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+        out[c] = h;
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t nthreads = std::min<uint32_t>(chunks, std::min<unsigned>(hw, 64u));
+    if (nthreads <= 1) {
+        for (uint32_t c = 0; c < chunks; ++c) one(c);
+        return VPB_OK;
+    }
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nthreads; ++t)
+        pool.emplace_back([=] { for (uint32_t c = t; c < chunks; c += nthreads) one(c); });
+    for (auto& th : pool) th.join();
     return VPB_OK;
 }
 
@@ -396,7 +444,17 @@ static int finish_timing() {
     return VPB_OK;
 }
 
+// Mesh::FacesCoords of a HOST mesh must index Mesh::Coords: an OBJ with a face reference the importer could not parse (or a
+// 0 / negative index) would otherwise make tri_setup read verts[3 * 0xFFFFFFFF] on the device and poison the context.
+static int check_indices(const uint32_t* tris, uint64_t n_tris, uint64_t n_verts) {
+    uint32_t mx = 0;
+    for (uint64_t i = 0; i < 3 * n_tris; ++i) mx = tris[i] > mx ? tris[i] : mx;
+    VPB_REQUIRE(n_tris == 0 || mx < n_verts, "mesh: face index %u out of range (%llu vertices)", mx, (unsigned long long)n_verts);
+    return VPB_OK;
+}
+
 static int upload_mesh(const float* verts, uint64_t n_verts, const uint32_t* tris, uint64_t n_tris, cudaStream_t st) {
+    VPB_TRY(check_indices(tris, n_tris, n_verts));
     VPB_TRY(g_ctx.verts.reserve(n_verts * 12 + 16));
     VPB_TRY(g_ctx.tris.reserve(n_tris * 12 + 16));
     if (n_verts) VPB_CUDA(cudaMemcpyAsync(g_ctx.verts.p, verts, n_verts * 12, cudaMemcpyHostToDevice, st));

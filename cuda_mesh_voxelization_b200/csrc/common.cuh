@@ -47,6 +47,25 @@ static inline uint64_t grid_words(uint32_t n) { return words_for_bits((uint64_t)
 
 int num_sms();
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per DEVICE (and vpb_init may move the library to
+// another device), so every launch site remembers which devices it has configured and for how many bytes.
+struct SmemOptIn {
+    uint64_t devices = 0;
+    size_t bytes = 0;
+    template <typename Kernel>
+    int ensure(Kernel kernel, size_t want) {
+        int dev = 0;
+        VPB_CUDA(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(devices & bit) || want > bytes) {
+            VPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            devices = want > bytes ? bit : (devices | bit);
+            bytes = want > bytes ? want : bytes;
+        }
+        return VPB_OK;
+    }
+};
+
 // ---- JFA state: the packed integer coordinates of a voxel's current nearest seed, 0 = "no seed" (also what zero-fill
 // produces outside the grid).  Two widths, chosen per translation unit (jfa.cu, jfa_flood4.cu and jfa_lattice.cu are
 // compiled twice, the second time with -DVPB_STATE64 and every exported name suffixed _s64):
@@ -146,5 +165,8 @@ int jfa_pass_launch_s64(const uint32_t* below, const uint32_t* mid, const uint32
                         cudaStream_t st);
 int jfa_finalize_launch_s64(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
                             float* sdf, uint32_t* seeds, cudaStream_t st);
+
+void jfa_lut_release();
+void jfa_lut_release_s64();
 
 }  // namespace vpb

@@ -198,25 +198,67 @@ unsigned grid_for(uint64_t items) {
 
 }  // namespace
 
-// One 12 / 24 KB device buffer per process and state width (the library serves one caller thread / one frame at a time,
-// like vplib).  Rebuilt on every pass launch: 3 us, stream-ordered before the pass that reads it.
+// The px | py | pz tables of a frame (12 / 24 KB).  Built once per (device, frame) and kept in a small ring of slots per
+// device, so a step launches the table kernel once instead of once per pass (13 launches per 1024^3 step before).  A
+// pass on another stream than the one that built the table waits for the build through an event; a slot is only
+// recycled after four other frames have been used on the device (callers serve one frame at a time, like vplib).
+namespace {
+struct LutSlot {
+    float* lut = nullptr;
+    cudaEvent_t built = nullptr;
+    cudaStream_t stream = nullptr;
+    Frame f{0, 0, 0, 0, 0};
+    uint64_t stamp = 0;
+};
+constexpr int LUT_DEVICES = 16, LUT_SLOTS = 4;
+LutSlot g_lut[LUT_DEVICES][LUT_SLOTS];
+uint64_t g_lut_clock = 0;
+bool same_frame(const Frame& a, const Frame& b) {
+    return memcmp(&a.ox, &b.ox, sizeof(float) * 4) == 0;   // origin + voxel size, bit for bit (n does not enter the tables)
+}
+}  // namespace
+
 const float* VPB_SFX(jfa_lut_launch)(const Frame& f, cudaStream_t st) {
-    static float* lut = nullptr;
-    static int lut_device = -1;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (!lut || lut_device != dev) {
-        if (cudaMalloc(&lut, 3 * MAX_N * sizeof(float)) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= LUT_DEVICES) { set_error("jfa: bad device for the position tables"); return nullptr; }
+    LutSlot* slots = g_lut[dev];
+    LutSlot* victim = &slots[0];
+    for (int i = 0; i < LUT_SLOTS; ++i) {
+        LutSlot& s = slots[i];
+        if (s.lut && same_frame(s.f, f)) {
+            s.stamp = ++g_lut_clock;
+            if (s.stream != st && cudaStreamWaitEvent(st, s.built, 0) != cudaSuccess) { set_error("jfa: table event wait failed"); return nullptr; }
+            return s.lut;
+        }
+        if (s.stamp < victim->stamp) victim = &s;
+    }
+    LutSlot& s = *victim;
+    if (!s.lut) {
+        if (cudaMalloc(&s.lut, 3 * MAX_N * sizeof(float)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.built, cudaEventDisableTiming) != cudaSuccess) {
             set_error("jfa: cannot allocate the position tables");
-            lut = nullptr;
+            cudaGetLastError();
+            if (s.lut) cudaFree(s.lut);
+            s.lut = nullptr;
             return nullptr;
         }
-        lut_device = dev;
     }
-    jfa_lut_kernel<<<MAX_N / 256, 256, 0, st>>>(f, lut);
+    jfa_lut_kernel<<<MAX_N / 256, 256, 0, st>>>(f, s.lut);
     count_launch();
-    if (cudaPeekAtLastError() != cudaSuccess) { set_error("jfa_lut_kernel launch failed"); return nullptr; }
-    return lut;
+    if (cudaPeekAtLastError() != cudaSuccess || cudaEventRecord(s.built, st) != cudaSuccess) { set_error("jfa_lut_kernel launch failed"); return nullptr; }
+    s.f = f; s.stream = st; s.stamp = ++g_lut_clock;
+    return s.lut;
+}
+
+// vpb_shutdown: the tables of the current device
+void VPB_SFX(jfa_lut_release)() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= LUT_DEVICES) return;
+    for (LutSlot& s : g_lut[dev]) {
+        if (s.lut) cudaFree(s.lut);
+        if (s.built) cudaEventDestroy(s.built);
+        s = LutSlot{};
+    }
 }
 
 #ifndef VPB_STATE64

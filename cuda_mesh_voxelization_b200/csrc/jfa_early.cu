@@ -278,11 +278,8 @@ jfa_early(const EarlyArgs a) {
 template <int G, int THREADS>
 int launch(const EarlyArgs& a, uint32_t n_rz, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)PTS * G * (sizeof(state_t) + 4 + 2);
-    static bool configured = false;
-    if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_early<G, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    { const int rc = optin.ensure(jfa_early<G, THREADS>, SMEM); if (rc != VPB_OK) return rc; }
     dim3 grid(a.K / G, a.K, n_rz);
     jfa_early<G, THREADS><<<grid, THREADS, SMEM, st>>>(a);
     VPB_LAUNCH_CHECK();

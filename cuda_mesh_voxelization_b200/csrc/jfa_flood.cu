@@ -379,12 +379,9 @@ size_t smem_bytes(int rows, int W) { return ((size_t)3 * MAXN + (size_t)10 * row
 
 template <int SS, bool FINAL>
 int launch_one(const FloodArgs& a, dim3 grid, cudaStream_t st) {
-    static size_t configured = 0;
+    static SmemOptIn optin;
     const size_t bytes = smem_bytes(a.rows, Tile<SS>::W);
-    if (bytes > configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_flood<SS, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
-    }
+    { const int rc = optin.ensure(jfa_pass_flood<SS, FINAL>, bytes); if (rc != VPB_OK) return rc; }
     jfa_pass_flood<SS, FINAL><<<grid, THREADS, bytes, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;

@@ -475,11 +475,8 @@ jfa_pass_flood4(const F4Args a) { Flood4<SS, TR, FINAL>::run(a); }
 template <int SS, int TR, bool FINAL>
 int launch_one(const F4Args& a, dim3 grid, cudaStream_t st) {
     using C = Cfg<SS, TR>;
-    static bool configured = false;
-    if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_flood4<SS, TR, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    { const int rc = optin.ensure(jfa_pass_flood4<SS, TR, FINAL>, C::SMEM); if (rc != VPB_OK) return rc; }
     jfa_pass_flood4<SS, TR, FINAL><<<grid, C::THREADS, C::SMEM, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;

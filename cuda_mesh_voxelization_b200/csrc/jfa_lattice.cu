@@ -205,11 +205,8 @@ jfa_pass_lattice(const LatArgs a) {
 template <int L, bool LUT_SMEM>
 int launch(const LatArgs& a, dim3 grid, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)L * L * THREADS * (4 * sizeof(state_t) + 3 * sizeof(float)) + (LUT_SMEM ? 3 * MAXN : 0) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_lattice<L, LUT_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    { const int rc = optin.ensure(jfa_pass_lattice<L, LUT_SMEM>, SMEM); if (rc != VPB_OK) return rc; }
     jfa_pass_lattice<L, LUT_SMEM><<<grid, dim3(TX, TY), SMEM, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;

@@ -410,11 +410,8 @@ __global__ void __launch_bounds__(THREADS, VPB_MARCH_MINBLOCKS) jfa_pass_march(c
 template <int SS, bool FINAL, bool COL>
 int launch_one(const PassArgs& a, dim3 grid, cudaStream_t st) {
     using TL = Tile<SS>;
-    static bool configured = false;
-    if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(jfa_pass_march<SS, FINAL, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    { const int rc = optin.ensure(jfa_pass_march<SS, FINAL, COL>, TL::BYTES); if (rc != VPB_OK) return rc; }
     jfa_pass_march<SS, FINAL, COL><<<grid, THREADS, TL::BYTES, st>>>(a);
     VPB_LAUNCH_CHECK();
     return VPB_OK;

@@ -19,6 +19,8 @@
 //                      vplib layout afterwards
 #include "common.cuh"
 
+#include <cmath>
+
 namespace vpb {
 namespace {
 
@@ -261,6 +263,9 @@ int vox_launch(const float* verts, uint64_t n_verts, const uint32_t* tris, uint6
                uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch, size_t scratch_bytes, cudaStream_t st) {
     VPB_REQUIRE(f.n > 0 && z0 < z1 && z1 <= f.n, "voxelize: bad grid/slab (n=%u z0=%u z1=%u)", f.n, z0, z1);
     VPB_REQUIRE(n_tris < 0xFFFFFFFFull, "voxelize: too many triangles");
+    // a degenerate bounding box (voxel size 0, e.g. a single-point mesh through the CLI) would divide by zero in tri_setup
+    VPB_REQUIRE(f.vs > 0.0f && std::isfinite(f.vs) && std::isfinite(f.ox) && std::isfinite(f.oy) && std::isfinite(f.oz),
+                "voxelize: voxel size must be positive and finite, origin finite (vs=%g)", (double)f.vs);
     VPB_REQUIRE(words_slab && scratch, "voxelize: null buffer");
     VPB_REQUIRE(n_tris == 0 || (verts && tris && n_verts > 0), "voxelize: null mesh");
     const ScratchLayout l = layout(f.n, n_tris, z0, z1);

@@ -62,6 +62,12 @@ VPB_API uint64_t vpb_kernel_launches(void);
 /* Milliseconds of the stages of the last *_host / pipeline call, CUDA-event timed:
  * out[0] H2D, out[1] kernels, out[2] D2H.  Mirrors the reference's "[...::Memory]"/"[...::Processing]" split. */
 VPB_API int vpb_last_timing(float out[3]);
+/* FNV-1a-64 digests of a HOST buffer cut into `chunks` equal consecutive pieces (bytes % chunks == 0), one digest per
+ * piece in out[chunks], the pieces hashed by parallel host threads.  chunks == 1 is the digest SURVEY.md section 8c
+ * tabulates for the reference's grids (offset basis 1469598103934665603, prime 1099511628211).  bench.py uses it to print
+ * the digest of every z-slab of the final sdf so that 1/2/4/8-GPU runs can be compared with the reference's golden
+ * digests; no GPU work, no reference counterpart. */
+VPB_API int vpb_fnv1a64_chunks(const void* data, uint64_t bytes, uint32_t chunks, uint64_t* out);
 
 /* ---- host-buffer stage calls: what VOX/CSG/JFA::Compute bind to -------------------------------- */
 

@@ -1,6 +1,10 @@
 // OBJ import/export with the reference's dialect (vplib/src/mesh/mesh_io.cpp:15-131), header only.
-//   import: `v x y z [r g b]`, `vn x y z`, `f a//n b//n c//n` (exactly three refs, 1-based; the only face syntax the
-//           reference parses), `# Vertices: n` / `# Faces: n` pre-reserve; everything else is ignored.
+//   import: `v x y z [r g b]`, `vn x y z`, `f r r r` with exactly three whitespace-separated refs, 1-based; of each ref the
+//           reference reads the leading integer as the position index and, only for the `a//n` form, the normal index
+//           (sscanf " %d//%d" per token, mesh_io.cpp:60-72), so `a`, `a/t`, `a/t/n` and `a//n` all import with the right
+//           positions (for the first three the reference leaves the normal index at its previous value; here it is the
+//           position index).  `# Vertices: n` / `# Faces: n` pre-reserve; everything else is ignored.  A face index
+//           outside 1..#v makes the import fail (the reference would read out of bounds later).
 //   export: fixed 6 decimals; header with vertex count and QUAD count (FacesCoords.size()/6); `v x y z r g b` with
 //           8-bit colour / 255; blank line; `vn`; blank line; `f i//n j//n k//n`.
 // The importer is a single pass over the file buffer with strtof/strtoul (the reference's iostream parser takes
@@ -63,16 +67,33 @@ inline bool ImportMesh(const std::string& filename, Mesh& mesh) {
             }
         } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
             char* q = p + 1;
+            long a = 0, b = 0;
             for (int i = 0; i < 3; ++i) {
-                const unsigned long a = std::strtoul(q, &q, 10);
-                unsigned long b = a;
-                if (q[0] == '/' && q[1] == '/') { q += 2; b = std::strtoul(q, &q, 10); }
+                while (*q == ' ' || *q == '\t' || *q == '\r') ++q;
+                if (*q) {                               // a missing token repeats the previous one, like `ss >> str` failing
+                    char* t = q;
+                    const long v = std::strtol(t, &t, 10);
+                    if (t != q) {                       // leading integer = position index
+                        a = b = v;
+                        if (t[0] == '/' && t[1] == '/') {
+                            char* u = t + 2;
+                            const long w = std::strtol(u, &u, 10);
+                            if (u != t + 2) b = w;
+                        }
+                    }
+                    while (*q && *q != ' ' && *q != '\t' && *q != '\r') ++q;   // rest of the token (/t, /t/n) is not used
+                }
                 mesh.FacesCoords.push_back((uint32_t)(a - 1));
                 mesh.FacesNormals.push_back((uint32_t)(b - 1));
             }
         }
         p = eol + 1;
     }
+    for (const uint32_t idx : mesh.FacesCoords)
+        if (idx >= mesh.Coords.size()) {
+            std::fprintf(stderr, "[ERROR] %s: face index %u out of range (%zu vertices)\n", filename.c_str(), idx + 1u, mesh.Coords.size());
+            return false;
+        }
     mesh.Name = filename;
     return true;
 }

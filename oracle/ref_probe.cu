@@ -20,6 +20,8 @@
 #include <span>
 #include <vector>
 
+#include <omp.h>
+
 #include <bounding_box.h>
 #include <csg/csg.h>
 #include <grid/grid.h>
@@ -78,6 +80,11 @@ int vpref_import_mesh(const char* path, float** verts, uint64_t* n_verts, uint32
 }
 
 void vpref_free(void* p) { std::free(p); }
+
+// OpenMP team size of the reference's -t 3 back-ends (csg/openmp.cpp:21, jfa/openmp.cpp:25,76 use plain `parallel for`,
+// i.e. the runtime default).  bench.py sets it explicitly: under torchrun the environment carries OMP_NUM_THREADS=1.
+void vpref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int vpref_max_threads(void) { return omp_get_max_threads(); }
 
 // Grid frame exactly as the CLI derives it (main.cpp:73-86).
 int vpref_frame(const float* verts, uint64_t n_verts, uint32_t n, float* origin, float* voxel_size) {

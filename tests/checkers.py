@@ -152,7 +152,14 @@ class Reference:
         L.vpref_jfa.argtypes = [_u32p, ctypes.c_uint32, ctypes.c_float, _f32p, _f32p, ctypes.c_int]
         L.vpref_export.argtypes = [_u32p, _f32p, ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_int,
                                    ctypes.c_char_p]
+        L.vpref_set_threads.argtypes = [ctypes.c_int]
+        L.vpref_max_threads.restype = ctypes.c_int
         self.last_ms = 0.0
+
+    def set_threads(self, n: int) -> int:
+        """OpenMP team size of the -t 3 back-ends; returns omp_get_max_threads() afterwards."""
+        self.lib.vpref_set_threads(int(n))
+        return int(self.lib.vpref_max_threads())
 
     def import_mesh(self, path: str):
         v = _f32p()

@@ -31,6 +31,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_large():
+    """Digests of the reference's OpenMP JFA at 512^3 / 1024^3 (tests/golden/make_golden_large.py)."""
+    with open(os.path.join(HERE, "golden", "ref_digests_large.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from checkers import Oracle
     return Oracle()

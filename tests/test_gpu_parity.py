@@ -211,18 +211,79 @@ def test_tiled_pass_equals_gather_pass_and_oracle(mesh, n, meshes, oracle, vpb, 
         assert np.array_equal(seeds_t, _public_seeds(oseeds, n))
 
 
+def _large_case(rec, meshes, oracle):
+    from cuda_mesh_voxelization_b200 import meshgen
+    ms = [meshgen.bunny_with_faces(*meshes["bunny"], rec["faces"])]
+    if rec["second"]:
+        ms.append(meshes[rec["second"]])
+    n = rec["n"]
+    origin, vs = oracle.frame(np.concatenate([m[0] for m in ms]), n)
+    assert float(vs).hex() == rec["voxel_size_hex"] and [float(o).hex() for o in origin] == rec["origin_hex"]
+    return ms, n, origin, vs
+
+
+def _check_large(rec, words, sdf, vpb):
+    assert vpb.fnv_chunks(words, 1)[0] == rec["result"]["fnv"]
+    assert vpb.fnv_chunks(sdf, 8) == rec["sdf"]["fnv_z8"]
+    assert vpb.fnv_chunks(sdf, 1)[0] == rec["sdf"]["fnv"]
+    assert int((sdf == 0).sum()) == rec["sdf"]["seeds"]
+    assert float(sdf.min()).hex() == rec["sdf"]["min_hex"] and float(sdf.max()).hex() == rec["sdf"]["max_hex"]
+
+
+def test_config3_512_sdf_matches_reference_digest_and_gather_witness(golden_large, meshes, oracle, vpb, monkeypatch):
+    """BASELINE config 3 (1 348 128 faces, 512^3): the shipped path -- jfa_early<8> + jfa_pass_flood4<32,16>, <16,16>,
+    <8,16> .. <1,16> -- against the digest of the REFERENCE's own OpenMP JFA at this size (vplib/src/jfa/openmp.cpp:70-128),
+    and against the independent one-thread-per-voxel gather kernel (VPB_JFA_KERNEL=gather: separate seed kernel, no fused
+    early passes, no keys), sdf bits and nearest-seed indices."""
+    rec = golden_large["bunny1348128_n512"]
+    ms, n, origin, vs = _large_case(rec, meshes, oracle)
+    words = vpb.voxelize_host(*ms[0], n, vs, origin)
+    sdf, seeds = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    _check_large(rec, words, sdf, vpb)
+    monkeypatch.setenv("VPB_JFA_KERNEL", "gather")
+    sdf_g, seeds_g = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
+    monkeypatch.delenv("VPB_JFA_KERNEL")
+    assert np.array_equal(sdf.view(np.uint32), sdf_g.view(np.uint32))
+    assert np.array_equal(seeds, seeds_g)
+    # the host pipeline call (what the CLI's -t 4 path and bench.py's e2e use) gives the same bytes
+    words_p, sdf_p = vpb.pipeline_host(ms, n, vs, origin, op=0)
+    _check_large(rec, words_p, sdf_p, vpb)
+
+
+def test_metric_config_1024_sdf_matches_reference_digest(golden_large, meshes, oracle, vpb):
+    """The metric's own configuration (1024^3, 1 348 128-face bunny U bimba; jfa_early<8> + jfa_pass_flood4<64,16> ..
+    <1,16>, the kernels bench.py times): occupancy and SDF byte-identical to the reference's OpenMP path run once on the
+    GPU box's host (tests/golden/make_golden_large.py), through vpb_pipeline_host and through the device-resident
+    pipeline bench.py's `value` is measured on."""
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh, DevicePipeline
+    rec = golden_large["bunny1348128_union_bimba_n1024"]
+    ms, n, origin, vs = _large_case(rec, meshes, oracle)
+    words, sdf = vpb.pipeline_host(ms, n, vs, origin, op=rec["op"])
+    _check_large(rec, words, sdf, vpb)
+    del sdf
+    pipe = DevicePipeline(n, vs, origin)
+    pipe.run([DeviceMesh(*m, "cuda:0") for m in ms], op=capi.OP_UNION, sdf=True)
+    torch.cuda.synchronize()
+    assert vpb.fnv_chunks(pipe.sdf.cpu().numpy(), 8) == rec["sdf"]["fnv_z8"]
+    assert vpb.fnv_chunks(pipe.words_host(), 1)[0] == rec["result"]["fnv"]
+
+
 def test_lattice_first_passes_equal_flood_passes_512(meshes, oracle, vpb, monkeypatch):
-    """jfa_lattice.cu takes the k >= N/4 passes; with VPB_JFA_LATTICE=0 the flood kernels run them.  Same SDF and same
-    nearest seeds at 512^3 on the 1 348 128-face bunny (config 3), where the CPU oracle is too slow to ask."""
+    """With the fused early kernel switched off (VPB_JFA_EARLY=0) jfa_lattice.cu takes the k >= N/4 passes; with
+    VPB_JFA_LATTICE=0 as well the flood kernels run them.  Same SDF and same nearest seeds at 512^3 (config 3)."""
     from cuda_mesh_voxelization_b200 import meshgen
     v, t = meshgen.bunny_with_faces(*meshes["bunny"], 1348128)
     n = 512
     origin, vs = oracle.frame(v, n)
     words = vpb.voxelize_host(v, t, n, vs, origin)
+    monkeypatch.setenv("VPB_JFA_EARLY", "0")
     sdf_l, seeds_l = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
     monkeypatch.setenv("VPB_JFA_LATTICE", "0")
     sdf_f, seeds_f = vpb.jfa_host(words, n, vs, origin, want_seeds=True)
     monkeypatch.delenv("VPB_JFA_LATTICE")
+    monkeypatch.delenv("VPB_JFA_EARLY")
     assert np.array_equal(sdf_l.view(np.uint32), sdf_f.view(np.uint32))
     assert np.array_equal(seeds_l, seeds_f)
 
