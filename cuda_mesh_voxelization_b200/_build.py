@@ -8,7 +8,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libvpb200.so")
-SOURCES = ["capi.cu", "vox.cu", "vox_surface.cu", "csg.cu", "jfa.cu", "jfa_tiled.cu", "jfa_flood.cu", "jfa_flood4.cu", "jfa_lattice.cu", "jfa_early.cu"]
+SOURCES = ["capi.cu", "vox.cu", "vox_surface.cu", "csg.cu", "jfa.cu", "jfa_tiled.cu", "jfa_flood.cu", "jfa_flood4.cu", "jfa_flood5.cu", "jfa_lattice.cu", "jfa_early.cu"]
 # compiled a second time with -DVPB_STATE64: the 64-bit seed state of grids above 1024^3 (csrc/common.cuh)
 SOURCES_S64 = ["jfa.cu", "jfa_flood4.cu", "jfa_lattice.cu", "jfa_early.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "vpb200.h")]

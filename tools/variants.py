@@ -7,12 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "cuda_mesh_voxelization_b200", "build", "variants")
 VARIANTS = {
-    "base": [],
-    "mb2": ["-DVPB_FLOOD_MINBLOCKS=2"],
-    "mb4": ["-DVPB_FLOOD_MINBLOCKS=4"],
-    "lz64": ["-DVPB_FLOOD_LZ=64"],
-    "mb4_lz64": ["-DVPB_FLOOD_MINBLOCKS=4", "-DVPB_FLOOD_LZ=64"],
+    "f5_r2": ["-DVPB_F5_RPT=2"],
+    "f5_r4": ["-DVPB_F5_RPT=4"],
+    "f5_r4_c3": ["-DVPB_F5_RPT=4", "-DVPB_F5_CTAS=3"],
 }
+if os.environ.get("VPB_VARIANT_FLAGS"):
+    VARIANTS = {k: v + os.environ["VPB_VARIANT_FLAGS"].split() for k, v in VARIANTS.items()}
 if sys.argv[1] == "build":
     from cuda_mesh_voxelization_b200 import _build
     os.makedirs(VDIR, exist_ok=True)
@@ -20,12 +20,21 @@ if sys.argv[1] == "build":
         print(name, _build.build(force=True, extra_flags=flags, out=os.path.join(VDIR, f"libvpb200_{name}.so")))
 elif sys.argv[1] == "run":
     n = sys.argv[2] if len(sys.argv) > 2 else "512"
+    tests = os.environ.get("VPB_VARIANT_TESTS")
     for name in VARIANTS:
+        if tests:
+            env = dict(os.environ, VPB_LIB=os.path.join(VDIR, f"libvpb200_{name}.so"))
+            r = subprocess.run(["timeout", "900", sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q", "-k", tests],
+                               env=env, capture_output=True, text=True, cwd=ROOT)
+            print(name, "pytest:", r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
+            if r.returncode != 0:
+                print(r.stdout[-3000:], flush=True)
         env = dict(os.environ, VPB_LIB=os.path.join(VDIR, f"libvpb200_{name}.so"))
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n", n, "--steps", "3", "--warmup", "2", "--no-cpu-baseline"],
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n", n, "--steps", "3", "--warmup", "3", "--no-cpu-baseline"],
                              env=env, capture_output=True, text=True)
         try:
             d = json.loads(out.stdout.strip().splitlines()[-1])
-            print(name, "ms/step %.2f" % d["ms_per_step"], {k: round(v, 2) for k, v in d["roofline"]["ms_per_pass_by_k"].items()}, flush=True)
+            print(name, "ms/step %.2f" % d["ms_per_step"], {k: round(v, 2) for k, v in d["roofline"]["ms_per_pass_by_k"].items()},
+                  "parity", d.get("parity", {}).get("status"), flush=True)
         except Exception as e:
             print(name, "FAILED", e, out.stderr[-400:])
