@@ -199,6 +199,54 @@ def workload_name(args):
             f"{args.op} + JFA SDF at {args.n}^3")
 
 
+def extra_run(args, n, op_name, rank, world, dev, barrier, steps=3, warmup=2):
+    """One more device-resident measurement in the same process (multi-GPU only): same meshes, another grid side / CSG
+    operator.  Returns a small record for config.extra_runs (ms per step = max over ranks of the CUDA-event time, the
+    per-rank stage table, and an order-independent checksum of the sdf bit patterns summed over the ranks)."""
+    import torch
+    import torch.distributed as dist
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    from cuda_mesh_voxelization_b200.multi import SlabPipeline
+    meshes, origin, vs = load_workload(n, args.faces)
+    pipe = SlabPipeline(n, vs, origin, rank, world, device=dev)
+    dm = [DeviceMesh(v, t, dev) for v, t in meshes]
+    op = OPS[op_name][0]
+    for _ in range(warmup):
+        pipe.run(dm, op=op, sdf=True)
+    barrier()
+    pipe.pass_events.clear()
+    pipe.early_events.clear()
+    pipe.stage_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pipe.run(dm, op=op, sdf=True, record_passes=True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    stage = {}
+    ev = pipe.stage_events
+    for (la, ea), (lb, eb) in zip(ev, ev[1:]):
+        if lb != "start":
+            stage[lb] = stage.get(lb, 0.0) + ea.elapsed_time(eb) / steps
+    keys = sorted(stage)
+    t = torch.tensor([stage[k_] for k_ in keys], device=dev)
+    allt = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    chk = pipe.sdf.view(torch.int32).to(torch.int64).sum().reshape(1)
+    dist.all_reduce(chk)
+    ms_step = float(ms.item()) / steps
+    rec = {"workload": f"bunny subdivided to {args.faces} faces {OPS[op_name][1]} bimba, solid voxelization + CSG {op_name} + JFA SDF at "
+                       f"{n}^3 (BASELINE config 5), {world} z-slabs", "n": n, "csg": op_name, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_step, "value": n ** 3 / (ms_step * 1e-3) / 1e9, "unit": UNIT,
+           "stage_ms_by_rank": {k_: [round(float(a[i]), 2) for a in allt] for i, k_ in enumerate(keys)},
+           "sdf_bits_checksum": int(chk.item())}
+    del pipe
+    torch.cuda.empty_cache()
+    return rec
+
+
 def golden_parity(args, digest):
     """Compares the run's sdf digests with the reference-generated ones (tests/golden/ref_digests_large.json, made by
     tests/golden/make_golden_large.py from the unmodified reference's OpenMP JFA).  "green" = every z-chunk of the final
@@ -243,7 +291,9 @@ def run_ours(args):
     dev = f"cuda:{local}"
     capi.init(local)
 
-    if world > 1:
+    from cuda_mesh_voxelization_b200.multi import slabs_for
+    replicas = world > 1 and slabs_for(n, world) == 1      # small grids are not sharded: every GPU runs its own job
+    if world > 1 and not replicas:
         from cuda_mesh_voxelization_b200.multi import SlabPipeline
         pipe = SlabPipeline(n, vs, origin, rank, world, device=dev)
     else:
@@ -283,7 +333,7 @@ def run_ours(args):
     launches = capi.kernel_launches() - launches0
 
     partition_label = None
-    if world > 1:
+    if world > 1 and not replicas:
         halo = {"push": "halo planes written into the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
                         "device-side barrier per pass",
                 "pull": "halo planes read from the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
@@ -295,7 +345,7 @@ def run_ours(args):
     pass_ms = {}
     for k, a, b in pipe.pass_events:
         pass_ms.setdefault(k, []).append(a.elapsed_time(b))
-    slab_voxels = pipe.slab_voxels if world > 1 else n ** 3
+    slab_voxels = pipe.slab_voxels if (world > 1 and not replicas) else n ** 3
     pass_avg = {k: float(np.mean(v)) for k, v in pass_ms.items()}
     mean_pass_ms = float(np.mean([np.mean(v) for v in pass_ms.values()])) if pass_ms else None
     early_ms = float(np.mean([a.elapsed_time(b) for a, b in pipe.early_events])) if pipe.early_events else None
@@ -307,7 +357,7 @@ def run_ours(args):
             if lb != "start":
                 stage_ms[lb] = stage_ms.get(lb, 0.0) + ea.elapsed_time(eb) / args.steps
     stage_ranks = None
-    if stage_ms and world > 1:
+    if stage_ms and world > 1 and not replicas:
         keys = sorted(stage_ms)
         t = torch.tensor([stage_ms[k_] for k_ in keys], device=dev)
         allt = [torch.empty_like(t) for _ in range(world)]
@@ -371,7 +421,7 @@ def run_ours(args):
                       "overlap step i's D2H; wall clock over all steps incl. the last download)",
                "sync_call": sync_call}
 
-    if world > 1 and n <= 1024:
+    if world > 1 and n <= 1024 and not replicas:
         # every rank: its own pinned host buffers, mesh upload, slab pipeline, download of ITS slab of the sdf and the
         # occupancy words over its own PCIe link (SlabPipeline.run_host); device-event timed, max over ranks
         pv = [torch.from_numpy(np.ascontiguousarray(v, np.float32)).pin_memory() for v, _ in meshes]
@@ -407,6 +457,13 @@ def run_ours(args):
                "api": f"SlabPipeline.run_host(overlap=True) on {world} ranks (pinned host buffers; every rank uploads the "
                       "meshes and downloads its own z-slab of the sdf + occupancy; step i+1's kernels overlap step i's D2H)"}
 
+    # ---- BASELINE config 5 beside the metric run when all 8 GPUs are there: CSG difference + JFA SDF at 2048^3, z-slabs
+    extra_runs = None
+    if world > 1 and (args.extra_2048 == "on" or (args.extra_2048 == "auto" and world == 8 and n == 1024)):
+        del pipe
+        torch.cuda.empty_cache()
+        extra_runs = [extra_run(args, 2048, "difference", rank, world, dev, barrier)]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -431,16 +488,19 @@ def run_ours(args):
                                  "sample": f"one step at {n_q}^3, -t 0 (sequential voxelization, CSG and JFA), {dq:.2f} s"}
 
     parity = golden_parity(args, digest)
-    value = n ** 3 * args.steps / (ms_total * 1e-3) / 1e9
+    jobs = world if replicas else 1
+    value = jobs * n ** 3 * args.steps / (ms_total * 1e-3) / 1e9
     transport = partition_label
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "n": n, "faces": args.faces, "csg": args.op,
                    "l2": f"per-step working set (2 x {esz * n ** 3 / 1e9:.1f} GB seed state + {4 * n ** 3 / 1e9:.1f} GB sdf) "
                          ">> 126 MB L2, no flush needed",
-                   "partition": "single GPU" if world == 1 else f"{world} z-slabs, {transport}",
+                   "partition": "single GPU" if world == 1 else (
+                       f"{world} replicas: grids up to 512^3 stay on one GPU (multi.slabs_for), every GPU runs its own job" if replicas
+                       else f"{world} z-slabs, {transport}"),
                    **({"stage_ms_rank0": stage_ms} if stage_ms else {}),
                    **({"stage_ms_by_rank": stage_ranks} if stage_ranks else {})},
         "roofline": {"bound": "hbm", "kernel": "jfa flood pass (mean over the flood passes of a step: k = N/16 .. 1 when the "
@@ -451,6 +511,8 @@ def run_ours(args):
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "digest": digest, "parity": parity,
     }
+    if extra_runs:
+        line["config"]["extra_runs"] = extra_runs
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -471,6 +533,9 @@ def main():
     ap.add_argument("--seq-n", type=int, default=256, help="grid side of the one -t 0 (sequential) CPU step timed beside "
                     "the OpenMP one in cpu_baseline (0 = skip; 256^3 is ~15-20 s on one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-2048", default="auto", choices=["auto", "on", "off"],
+                    help="also time BASELINE config 5 (difference + SDF at 2048^3) and report it under config.extra_runs; auto = "
+                         "when 8 GPUs run the default 1024^3 workload")
     args = ap.parse_args()
     if not args.ref_n:
         args.ref_n = 512

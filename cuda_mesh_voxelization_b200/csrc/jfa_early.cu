@@ -43,18 +43,13 @@ constexpr int MAXN = JFA_MAXN;
 constexpr int L = 8;                    // lattice points per axis after the three passes
 constexpr int PTS = L * L * L;
 constexpr uint32_t NOKEY = 0xFFFFFFFFu;
-// The kernel works on position tables multiplied by a power of two chosen on the host so that (K voxelSize)^2 lies in
-// [1, 4) (exact: every difference, product and sum of the distance scales by the same power of two, no denormals or
-// overflow are involved -- early_keys_ok); the smallest non-zero early distance is then > 2^-2 and the key base a
-// compile-time constant, so a key is ONE shift-add with an immediate: bits(d) * 32 + (code - (KEY_E0 << 23) * 32).
-constexpr uint32_t KEY_E0 = 125u;
-constexpr uint32_t KEY_K0 = 0u - (KEY_E0 << 23) * 32u;
 
 struct EarlyArgs {
     const uint32_t* shell;    // seed-shell bits of the FULL grid
     state_t* dst;             // state of the slab [z0, z1) after the passes k = N/2, N/4, N/8
-    const float* lut;         // px | py | pz of the SCALED frame (see KEY_E0)
+    const float* lut;         // px | py | pz
     uint32_t n, K, z0, z1;
+    uint32_t key_base;
     // distributed mode (T != 0): this launch runs the z residues rz0 .. rz0 + gridDim.z - 1 completely and stores every
     // plane z into the slab of its owner, rank z / T, at dst_rank[z / T] (device addresses valid in THIS process: the
     // owners' buffers mapped over NVLink); z0 = 0, z1 = n
@@ -91,44 +86,6 @@ __device__ __forceinline__ int c_off27(uint32_t k) {
     return dx * G + dy * (L * G) + dz * (L * L * G);
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// The 27 offers of one source at lattice stride S, fully unrolled with compile-time target offsets and codes:
-// I = c*9 + b*3 + aa, target = source + ((aa-1), (b-1), (c-1)) * S.  Per offer: one FADD (the reference's last addition),
-// one shift-add (key), one predicated shared-memory atomic.
-template <int G, int S, bool PRED, int I>
-struct Offer {
-    // valid: bit I set = target I lies inside the lattice (and in a plane this pass produces)
-    static __device__ __forceinline__ void run(uint32_t key_addr, const float (&XY)[3][3], const float (&Z)[3], uint32_t valid) {
-        constexpr int aa = I % 3, b = (I / 3) % 3, c = I / 9;
-        constexpr bool self = aa == 1 && b == 1 && c == 1;
-        // the target sees this source at offset (-(aa-1), -(b-1), -(c-1)): scan position of that offset
-        constexpr uint32_t code = self ? 0u : 1u + (uint32_t)((2 - c) * 9 + (2 - b) * 3 + (2 - aa));
-        constexpr int off = ((aa - 1) * G + (b - 1) * (L * G) + (c - 1) * (L * L * G)) * S * 4;   // bytes
-        const float d = __fadd_rn(XY[b][aa], Z[c]);                                             // ... + (dz*dz)
-        uint32_t kv = __float_as_uint(d) * 32u + (KEY_K0 + code);
-        if (self) kv = d == 0.0f ? code : kv;
-        if (PRED) {   // (ptxas turns the predicated shared atomic into a branch around it: BSSY / BRA / BSYNC per offer)
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                "and.b32 t, %2, %4;\n\t"
-                "setp.ne.u32 p, t, 0;\n\t"
-                "@p red.shared.min.u32 [%0+%3], %1;\n\t}"
-                ::"r"(key_addr), "r"(kv), "r"(valid), "n"(off), "n"(1 << I)
-                : "memory");
-        } else {      // interior source: all 27 targets exist -- FADD, shift-add, atomic
-            asm volatile("red.shared.min.u32 [%0+%2], %1;" ::"r"(key_addr), "r"(kv), "n"(off) : "memory");
-        }
-        Offer<G, S, PRED, I + 1>::run(key_addr, XY, Z, valid);
-    }
-};
-template <int G, int S, bool PRED>
-struct Offer<G, S, PRED, 27> {
-    static __device__ __forceinline__ void run(uint32_t, const float (&)[3][3], const float (&)[3], uint32_t) {}
-};
-
-template <int S> struct Stride { static constexpr int value = S; };
-
 // G = x-adjacent lattices per CTA.  Point index p = ((l * 8 + j) * 8 + i) * G + g  <->  voxel
 // (rx0 + g + i K, ry + j K, rz + l K).
 template <int G, int THREADS>
@@ -142,10 +99,7 @@ jfa_early(const EarlyArgs a) {
     state_t* const st = reinterpret_cast<state_t*>(smem_raw);            // [NP] current state
     uint32_t* const key = reinterpret_cast<uint32_t*>(st + NP);          // [NP] best key of the running pass
     uint16_t* const list = reinterpret_cast<uint16_t*>(key + NP);        // [NP] points that hold a seed
-    // the list of points that hold a seed is two-ended: INTERIOR points of the coming pass (all 27 targets inside the
-    // lattice and needed: no predicates, immediate offsets) from the front, the others from the back, so that warps of the
-    // push loop run one of the two bodies
-    __shared__ int s_count[2];
+    __shared__ int s_count;
     __shared__ int s_off27[27];
     if (threadIdx.x < 27) s_off27[threadIdx.x] = c_off27<G>(threadIdx.x);
 
@@ -160,63 +114,27 @@ jfa_early(const EarlyArgs a) {
     const int lo1 = a.z0 > rz ? (int)((a.z0 - rz + K - 1u) / K) : 0;
     const int hi1 = a.z1 > rz ? min(L - 1, (int)((a.z1 - 1u - rz) / K)) : -1;
     if (lo1 > hi1) return;                                 // no plane of this lattice lies in the slab (uniform per CTA)
-    if (tid < 2) s_count[tid] = 0;
+    if (tid == 0) s_count = 0;
     __syncthreads();
-    const bool full = lo1 == 0 && hi1 == L - 1;            // every plane of the lattice is wanted (single-GPU runs)
-    // quad m of this thread (4 x-adjacent lattices, one lattice point): interior for lattice stride S?
-    auto interior_quads = [&](int S) {
-        uint32_t msk = 0;
-        if (!full || S > 3) return msk;
-#pragma unroll
-        for (int m = 0; m < QPT; ++m) {
-            const int q = (4 * (tid + m * THREADS)) / G;
-            const int i = q & 7, j = (q >> 3) & 7, l = q >> 6;
-            const bool in = (unsigned)(i - S) <= (unsigned)(L - 1 - 2 * S) && (unsigned)(j - S) <= (unsigned)(L - 1 - 2 * S) &&
-                            (unsigned)(l - S) <= (unsigned)(L - 1 - 2 * S);
-            msk |= (in ? 15u : 0u) << (4 * m);
-        }
-        return msk;
-    };
 
-    // appends the thread's flagged points (bit m*4+u = point 4*(tid + m*THREADS) + u) to the front (end = 0) or the back
-    // (end = 1) of the list
-    // Entries are grouped by quad slot m inside a warp (one packed scan: four 8-bit counters), so that neighbouring list
-    // entries are neighbouring threads' points of the SAME slot -- consecutive addresses -- instead of one thread's four
-    // quads, which lie 4 * THREADS points apart, i.e. in the same shared-memory banks.
-    auto compact = [&](uint32_t flags, int end) {
-        static_assert(QPT <= 4, "the packed scan holds four 8-bit counters");
-        uint32_t mine = 0;
-#pragma unroll
-        for (int m = 0; m < QPT; ++m) mine |= (uint32_t)__popc((flags >> (4 * m)) & 15u) << (8 * m);
-        uint32_t incl = mine;
+    // appends the thread's flagged points (bit m*4+u = point 4*(tid + m*THREADS) + u) to the list
+    auto compact = [&](uint32_t flags) {
+        const int mine = __popc(flags);
+        int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;                   // no carries between the fields: a warp holds <= 128 points per slot
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        const int total = (int)((tot & 255u) + ((tot >> 8) & 255u) + ((tot >> 16) & 255u) + (tot >> 24));
         int base = 0;
-        if (lane == 31 && total) base = atomicAdd(&s_count[end], total);
+        if (lane == 31 && incl) base = atomicAdd(&s_count, incl);
         base = __shfl_sync(0xffffffffu, base, 31);
-        const uint32_t excl = incl - mine;
-#pragma unroll
-        for (int m = 0; m < QPT; ++m) {
-            int pos = base + (int)((excl >> (8 * m)) & 255u);
-            uint32_t f = (flags >> (4 * m)) & 15u;
-            while (f) {
-                const int u = __ffs(f) - 1;
-                f &= f - 1u;
-                list[end ? NP - 1 - pos : pos] = (uint16_t)(4 * (tid + m * THREADS) + u);
-                ++pos;
-            }
-            base += (int)((tot >> (8 * m)) & 255u);
+        int pos = base + incl - mine;
+        while (flags) {
+            const int b = __ffs(flags) - 1;
+            flags &= flags - 1u;
+            list[pos++] = (uint16_t)(4 * (tid + (b >> 2) * THREADS) + (b & 3));
         }
-    };
-    auto compact2 = [&](uint32_t flags, int S_next) {
-        const uint32_t in = interior_quads(S_next);
-        compact(flags & in, 0);
-        compact(flags & ~in, 1);
     };
 
     // ---- initial state from the shell bits; keys cleared; first list -----------------------------------------------
@@ -238,25 +156,25 @@ jfa_early(const EarlyArgs a) {
             *reinterpret_cast<uint4*>(key + p) = make_uint4(NOKEY, NOKEY, NOKEY, NOKEY);
             flags |= w << (4 * m);
         }
-        compact2(flags, 4);
+        compact(flags);
     }
 
-    // ---- three passes: lattice stride S = 4, 2, 1  (k = S * K), S a compile-time constant of each ------------------------
-    const uint32_t key_s = smem_u32(key);
-    auto pass = [&](auto stride) {
-        constexpr int S = decltype(stride)::value;
+    // ---- three passes: lattice stride S = 4, 2, 1  (k = S * K) --------------------------------------------------------
+#pragma unroll 1
+    for (int S = 4; S >= 1; S >>= 1) {
         __syncthreads();                                   // state, keys and list of this pass are in place
-        const int count_in = s_count[0], count_bd = s_count[1];
+        const int count = s_count;
         const int nlo = max(0, lo1 - (S - 1)), nspan = min(L - 1, hi1 + (S - 1)) - nlo;   // target planes this pass: nlo .. nlo + nspan
         // push: every point that holds a seed offers it to itself (code 0) and to its <= 26 lattice neighbours
-        auto push = [&](int p, auto interior) {
-            constexpr bool IN = decltype(interior)::value != 0;
+#pragma unroll 1
+        for (int e = tid; e < count; e += THREADS) {
+            const int p = list[e];
             const int g = p % G, q = p / G;
             const int i = q & 7, j = (q >> 3) & 7, l = q >> 6;
             bool xo[3], yo[3], zo[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) zo[d] = IN || (unsigned)(l + (d - 1) * S - nlo) <= (unsigned)nspan;
-            if (!(zo[0] || zo[1] || zo[2])) return;         // a source none of whose z-targets is needed
+            for (int d = 0; d < 3; ++d) zo[d] = (unsigned)(l + (d - 1) * S - nlo) <= (unsigned)nspan;
+            if (!(zo[0] || zo[1] || zo[2])) continue;      // a source none of whose z-targets is needed
             const state_t s = st[p];
             const float sx = __ldg(lut + jfa_x(s)), sy = __ldg(lut + MAXN + jfa_y(s)), sz = __ldg(lut + 2 * MAXN + jfa_z(s));
             const int x = (int)(rx0 + g) + i * (int)K, y = (int)ry + j * (int)K, z = (int)rz + l * (int)K;
@@ -264,8 +182,8 @@ jfa_early(const EarlyArgs a) {
             float X[3], Y[3], Z[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                xo[d] = IN || (unsigned)(i + (d - 1) * S) < (unsigned)L;
-                yo[d] = IN || (unsigned)(j + (d - 1) * S) < (unsigned)L;
+                xo[d] = (unsigned)(i + (d - 1) * S) < (unsigned)L;
+                yo[d] = (unsigned)(j + (d - 1) * S) < (unsigned)L;
                 X[d] = sqdiff(sx, __ldg(lut + (xo[d] ? x + (d - 1) * kk : x)));
                 Y[d] = sqdiff(sy, __ldg(lut + MAXN + (yo[d] ? y + (d - 1) * kk : y)));
                 Z[d] = sqdiff(sz, __ldg(lut + 2 * MAXN + (zo[d] ? z + (d - 1) * kk : z)));
@@ -278,26 +196,26 @@ jfa_early(const EarlyArgs a) {
             for (int b = 0; b < 3; ++b)
 #pragma unroll
                 for (int aa = 0; aa < 3; ++aa) XY[b][aa] = __fadd_rn(X[aa], Y[b]);                // (dx*dx)+(dy*dy)
-            // bit c*9 + b*3 + aa of `valid` = zo[c] && yo[b] && xo[aa] (the three spreads have no overlapping bits)
-            uint32_t valid = 0;
-            if (!IN) {
-                const uint32_t mx = (xo[0] ? 1u : 0u) | (xo[1] ? 2u : 0u) | (xo[2] ? 4u : 0u);
-                const uint32_t my = (yo[0] ? 1u : 0u) | (yo[1] ? 8u : 0u) | (yo[2] ? 64u : 0u);
-                const uint32_t mz = (zo[0] ? 1u : 0u) | (zo[1] ? 512u : 0u) | (zo[2] ? 262144u : 0u);
-                valid = mx * my * mz;
-            }
-            Offer<G, S, !IN, 0>::run(key_s + 4u * (uint32_t)p, XY, Z, valid);
-        };
-        if (S < 4) {
-#pragma unroll 1
-            for (int e = tid; e < count_in; e += THREADS) push(list[e], Stride<1>{});
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                    for (int aa = 0; aa < 3; ++aa) {
+                        // the target sees this source at offset (-(aa-1), -(b-1), -(c-1)): scan position of that offset
+                        const bool self = aa == 1 && b == 1 && c == 1;
+                        const uint32_t code = self ? 0u : 1u + (uint32_t)((2 - c) * 9 + (2 - b) * 3 + (2 - aa));
+                        const float d = __fadd_rn(XY[b][aa], Z[c]);                               // ... + (dz*dz)
+                        uint32_t kv = ((__float_as_uint(d) - a.key_base) << 5) | code;
+                        if (self) kv = d == 0.0f ? code : kv;
+                        const int t = p + ((aa - 1) * G + (b - 1) * (L * G) + (c - 1) * (L * L * G)) * S;
+                        if (zo[c] && yo[b] && xo[aa]) atomicMin(key + t, kv);                     // predicated, no branch
+                    }
+                }
         }
-#pragma unroll 1
-        for (int e = tid; e < count_bd; e += THREADS) push(list[NP - 1 - e], Stride<0>{});
         __syncthreads();                                   // all keys final
-        if (tid < 2) s_count[tid] = 0;
-        // resolve, part 1: points whose winner is a neighbour fetch that neighbour's OLD state.  A quad none of whose keys
-        // was touched (most of them in the two sparse passes) costs one vector load and one test.
+        if (tid == 0) s_count = 0;
+        // resolve, part 1: points whose winner is a neighbour fetch that neighbour's OLD state
         state_t fresh[QPT][4];
         uint32_t held = 0, moved = 0;                       // per point: holds a seed after this pass / state changes
 #pragma unroll
@@ -307,35 +225,32 @@ jfa_early(const EarlyArgs a) {
             for (int u = 0; u < 4; ++u) fresh[m][u] = 0;
             if ((unsigned)(p / (L * L * G) - nlo) > (unsigned)nspan) continue;   // plane not produced by this pass (warp-uniform)
             const uint4 k4 = *reinterpret_cast<const uint4*>(key + p);
-            if ((k4.x & k4.y & k4.z & k4.w) == NOKEY) continue;
             const uint32_t kq[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool has = kq[u] != NOKEY;
+                if (kq[u] == NOKEY) continue;
+                held |= 1u << (4 * m + u);
                 const uint32_t code = kq[u] & 31u;
-                const bool mv = has && code != 0u;
-                held |= (has ? 1u : 0u) << (4 * m + u);
-                moved |= (mv ? 1u : 0u) << (4 * m + u);
-                // code - 1 = (dz+1)*9 + (dy+1)*3 + (dx+1)  ->  point offset of that neighbour at stride 1 (table)
-                if (mv) fresh[m][u] = st[p + u + s_off27[code - 1u] * S];
+                if (code == 0u) continue;
+                // code - 1 = (dz+1)*9 + (dy+1)*3 + (dx+1)  ->  point offset of that neighbour at stride 1 (table: the
+                // division chain was 16 % of the kernel's instructions, profiles/r01_v11_flood_summary.txt)
+                fresh[m][u] = st[p + u + s_off27[code - 1u] * S];
+                moved |= 1u << (4 * m + u);
             }
         }
         __syncthreads();                                   // every old state has been read
-        // resolve, part 2: store the changed states, clear the touched keys, list of the next pass
+        // resolve, part 2: store the changed states, clear the keys, list of the next pass
 #pragma unroll
         for (int m = 0; m < QPT; ++m) {
             const int p = 4 * (tid + m * THREADS);
-            if (!((held >> (4 * m)) & 15u)) continue;      // untouched quad: its keys are still NOKEY
+            if ((unsigned)(p / (L * L * G) - nlo) > (unsigned)nspan) continue;   // its keys were never touched and never will be
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((moved >> (4 * m + u)) & 1u) st[p + u] = fresh[m][u];
             if (S > 1) *reinterpret_cast<uint4*>(key + p) = make_uint4(NOKEY, NOKEY, NOKEY, NOKEY);
         }
-        if (S > 1) compact2(held, S / 2);
-    };
-    pass(Stride<4>{});
-    pass(Stride<2>{});
-    pass(Stride<1>{});
+        if (S > 1) compact(held);
+    }
     __syncthreads();
 
     // ---- the slab's part of the result ----------------------------------------------------------------------------
@@ -376,7 +291,7 @@ int launch(const EarlyArgs& a, uint32_t n_rz, cudaStream_t st) {
 // on every axis and the grid is at most 1.01 N vs wide.  Then two positions whose indices differ by m K (m >= 1) are
 // at least 0.74 K vs apart, so every non-zero early distance is in [0.5 (K vs)^2, 200 (K vs)^2]: with
 // 2^E0 <= (K vs)^2 / 4 the rebased bit pattern is in [1, 12 * 2^23) < 2^27.
-bool early_keys_ok(const Frame& f, uint32_t K, Frame* scaled) {
+bool early_keys_ok(const Frame& f, uint32_t K, uint32_t* key_base) {
     const float vs = f.vs;
     if (!(vs > 0.0f) || !std::isfinite(vs)) return false;
     volatile float kvs = (float)K * vs;
@@ -404,29 +319,24 @@ bool early_keys_ok(const Frame& f, uint32_t K, Frame* scaled) {
         volatile float width = prev - first;
         if (!(width <= 1.01f * (float)f.n * vs)) return false;
     }
-    // power of two 2^sh with (K vs 2^sh)^2 in [1, 4): (K vs)^2 in [2^t, 2^(t+1)), t = E0 - 125  ->  sh = ceil(-t / 2)
-    const int t = E0 - 125;
-    const int sh = t <= 0 ? (-t + 1) / 2 : -(t / 2);
-    const float sc = std::ldexp(1.0f, sh);
-    *scaled = Frame{f.ox * sc, f.oy * sc, f.oz * sc, f.vs * sc, f.n};          // exact
-    if (!std::isfinite(scaled->ox) || !std::isfinite(scaled->oy) || !std::isfinite(scaled->oz) || !(scaled->vs > 1e-30f)) return false;
+    *key_base = (uint32_t)E0 << 23;
     return true;
 }
 
 }  // namespace
 
 // Does the fused kernel take this grid?  (shape, frame, VPB_JFA_EARLY switch; the state pointer's alignment is checked at launch)
-static bool early_supported(const Frame& f, Frame* scaled) {
+static bool early_supported(const Frame& f, uint32_t* key_base) {
     const uint32_t n = f.n;
     const char* env = getenv("VPB_JFA_EARLY");
     if (env && strcmp(env, "0") == 0) return false;
     if (getenv("VPB_JFA_KERNEL")) return false;          // a forced pass kernel means "every pass through that kernel"
     if (n > (uint32_t)MAXN || n < 64u || n % 64u != 0) return false;
-    return early_keys_ok(f, n / 8u, scaled);
+    return early_keys_ok(f, n / 8u, key_base);
 }
 int VPB_SFX(jfa_early_supported)(const Frame& f) {
-    Frame scaled;
-    return early_supported(f, &scaled) ? 1 : 0;
+    uint32_t kb;
+    return early_supported(f, &kb) ? 1 : 0;
 }
 
 // Seed state after the passes k = N/2, N/4, N/8 for the slab [z0, z1), from the occupancy bits of the full grid;
@@ -437,8 +347,7 @@ int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32
                               uint32_t* state_, cudaStream_t st) {
     const uint32_t n = f.n;
     EarlyArgs a;
-    Frame scaled;
-    if (!early_supported(f, &scaled) || z0 >= z1 || z1 > n) return 1;
+    if (!early_supported(f, &a.key_base) || z0 >= z1 || z1 > n) return 1;
     if ((reinterpret_cast<uintptr_t>(state_) & 15u) != 0) return 1;
     VPB_REQUIRE(words_full && shell_scratch && state_, "jfa_early: null buffer");
     { const int rc = shell_launch(words_full, n, shell_scratch, st); if (rc != VPB_OK) return rc; }
@@ -448,7 +357,7 @@ int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32
     a.n = n; a.z0 = z0; a.z1 = z1;
     a.rz0 = 0; a.T = 0;
     for (auto& d : a.dst_rank) d = nullptr;
-    a.lut = VPB_SFX(jfa_lut_launch)(scaled, st);
+    a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
     const char* env = getenv("VPB_JFA_EARLY");
     const bool g16 = env && strcmp(env, "16") == 0 && a.K % 16u == 0;
@@ -464,8 +373,7 @@ int VPB_SFX(jfa_early_dist_launch)(const uint32_t* words_full, const Frame& f, u
                                    uint32_t* shell_scratch, cudaStream_t st) {
     const uint32_t n = f.n;
     EarlyArgs a;
-    Frame scaled;
-    if (!early_supported(f, &scaled)) return 1;
+    if (!early_supported(f, &a.key_base)) return 1;
     VPB_REQUIRE(words_full && shell_scratch && slab_states, "jfa_early_dist: null buffer");
     VPB_REQUIRE(world >= 1 && world <= 8 && slab_planes * world == n, "jfa_early_dist: %u slabs of %u planes do not tile N=%u", world, slab_planes, n);
     a.K = n / 8u;
@@ -479,7 +387,7 @@ int VPB_SFX(jfa_early_dist_launch)(const uint32_t* words_full, const Frame& f, u
     a.dst = nullptr;
     a.n = n; a.z0 = 0; a.z1 = n;
     a.rz0 = rz_lo; a.T = slab_planes;
-    a.lut = VPB_SFX(jfa_lut_launch)(scaled, st);
+    a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
     return launch<8, 256>(a, rz_hi - rz_lo, st);
 }

@@ -102,6 +102,19 @@ class SlabPlan:
         return out
 
 
+def slabs_for(n: int, world: int) -> int:
+    """How many z-slabs a job of side n should be cut into on `world` GPUs (last row): grids up to
+    512^3 stay on ONE GPU -- a 512^3 step is ~8 ms of kernels, less than the per-pass barriers and halo copies of a
+    sharded run would add -- and `world` GPUs then serve `world` independent jobs (replicas).  Larger grids use every GPU
+    that divides N."""
+    if n <= 512 or world <= 1:
+        return 1
+    w = world
+    while w > 1 and n % w:
+        w -= 1
+    return w
+
+
 # ----------------------------------------------------------------------------------------- GPU pipeline
 
 def _ptr(t):
@@ -164,6 +177,7 @@ class SlabPipeline:
                 print(f"[vpb200] peer mode unavailable ({type(e).__name__}: {e}); using the NCCL halo exchange", file=sys.stderr)
                 self.peer = False
         self.dma = False
+        self.overlap_halo = False
         if not self.peer:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
             want_dma = (comm is None and world > 1 and os.environ.get("VPB_HALO", "push") != "nccl"
@@ -230,6 +244,11 @@ class SlabPipeline:
         self.dist_early = (self.use_early and (self.n // 8) % p.world == 0 and os.environ.get("VPB_EARLY_DIST", "1") != "0")
         self.side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         self.side_done = [torch.cuda.Event() for _ in range(2)]
+        # the exchange of pass i+1 behind the interior of pass i (flood_overlapped).  Opt-in (VPB_HALO_OVERLAP=1): measured on
+        # 2 x B200 at 1024^3 it hides half of the exchange (0.89 -> 0.47 ms per step) but the two boundary launches march one
+        # plane per z-lattice column (three staged planes per output instead of ~1.1) and cost 1.7 ms more than they save:
+        # 34.7 against 33.4 ms per step (profiles/r02_multi_gpu_notes.md)
+        self.overlap_halo = os.environ.get("VPB_HALO_OVERLAP", "0") == "1"
 
     def peer_barrier(self, i):
         """All ranks have finished what they launched so far on buffer pair i (device-side, on the current stream)."""
@@ -380,6 +399,55 @@ class SlabPipeline:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
+    def flood_sub(self, k, cur, lo, hi):
+        """The pass with step k for the slab-local planes [lo, hi) only (extended-buffer mode: the source planes around
+        them are contiguous).  Used to compute the planes the neighbours need next BEFORE the rest of the slab."""
+        p, n = self.plan, self.n
+        if hi <= lo:
+            return
+        mid = self.center(cur).data_ptr() + lo * self.plane * 4
+        kb = k * self.plane * 4
+        dst = self.center(1 - cur).data_ptr() + lo * self.plane * 4
+        self.capi.check(self.lib.vpb_jfa_pass_dev(ctypes.c_void_p(mid - kb), ctypes.c_void_p(mid), ctypes.c_void_p(mid + kb),
+                                                  ctypes.c_void_p(dst), n, p.z0 + lo, p.z0 + hi, k, self.vs, self._o(),
+                                                  None, None, None, self._stream()))
+
+    def flood_overlapped(self, k, nxt, cur, record=False):
+        """One pass with the halo exchange of the NEXT pass (step nxt) hidden behind it (push mode).  The nxt planes at
+        either end of the slab -- what the neighbours need next -- are computed first; copy engines then write them into
+        the neighbours' halo regions of the destination buffer on two side streams while the interior of the slab is
+        computed; the device-side barrier that follows says that every rank's halos are complete.  A neighbour's halo
+        regions of that buffer were last read in the previous pass, which ended with the previous barrier."""
+        torch, p = self.torch, self.plan
+        main = torch.cuda.current_stream()
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        dstbuf = 1 - cur
+        self.flood_sub(k, cur, 0, nxt)
+        self.flood_sub(k, cur, p.T - nxt, p.T)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        centre = self.center(dstbuf)
+        for i, t in enumerate(p.sends(nxt)):
+            lo = (p.H - nxt) * self.plane if t.role == "below" else (p.H + p.T) * self.plane
+            st = self.side[i]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                self.peer_ext[dstbuf][t.peer][lo:lo + nxt * self.plane].copy_(
+                    centre[t.src_lo * self.plane:(t.src_lo + t.count) * self.plane], non_blocking=True)
+                self.side_done[i].record(st)
+        self.flood_sub(k, cur, nxt, p.T - nxt)
+        if record:
+            e1.record()
+            self.pass_events.append((k, e0, e1))
+        self._mark(record, "flood")
+        for i, _ in enumerate(p.sends(nxt)):
+            main.wait_event(self.side_done[i])
+        self.symm[dstbuf].barrier(channel=0)
+        self._mark(record, "exchange")
+
     def flood(self, k, cur, last, record=False):
         p, n = self.plan, self.n
         if self.peer:
@@ -457,11 +525,20 @@ class SlabPipeline:
             self.seed()
             cur = 0
         self._mark(record_passes, "seed")
-        for k in self.steps:
-            self.exchange(k, cur)
-            self._mark(record_passes, "exchange")
-            self.flood(k, cur, last=(k == 1), record=record_passes)
-            self._mark(record_passes, "flood")
+        overlap = self.dma == "push" and self.overlap_halo
+        halos_ready = False
+        for idx, k in enumerate(self.steps):
+            if not halos_ready:
+                self.exchange(k, cur)
+                self._mark(record_passes, "exchange")
+            nxt = self.steps[idx + 1] if idx + 1 < len(self.steps) else None
+            if overlap and nxt is not None and 2 * nxt <= p_.T and k < p_.T:
+                self.flood_overlapped(k, nxt, cur, record=record_passes)    # leaves the next pass's halos in place
+                halos_ready = True
+            else:
+                self.flood(k, cur, last=(k == 1), record=record_passes)
+                self._mark(record_passes, "flood")
+                halos_ready = False
             cur = 1 - cur
 
     def sdf_host(self):
