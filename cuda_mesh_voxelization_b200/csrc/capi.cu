@@ -60,7 +60,7 @@ struct Context {
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float timing[3] = {0, 0, 0};
-    Buf verts, tris, grid_a, grid_b, scratch, state_a, state_b, sdf, seeds;
+    Buf verts, tris, grid_a, grid_b, grid_c, scratch, state_a, state_b, sdf, seeds;
     // asynchronous pipeline (vpb_pipeline_submit / vpb_pipeline_wait): two jobs in flight, each slot owns the device
     // copies of its results so that the next job's kernels can run while this one's D2H is still going
     Buf slot_words[2], slot_sdf[2];
@@ -93,10 +93,14 @@ int seed_any(const uint32_t* words, uint32_t n, uint32_t z0, uint32_t z1, uint32
     return jfa_state64(n) ? jfa_seed_launch_s64(words, n, z0, z1, state, st) : jfa_seed_launch(words, n, z0, z1, state, st);
 }
 int early_any(const uint32_t* words, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch, uint32_t* state,
-              cudaStream_t st) {
+              cudaStream_t st, bool shell_ready = false) {
+    if (shell_ready)
+        return jfa_state64(f.n) ? jfa_early_from_shell_launch_s64(shell_scratch, f, z0, z1, state, st)
+                                : jfa_early_from_shell_launch(shell_scratch, f, z0, z1, state, st);
     return jfa_state64(f.n) ? jfa_early_launch_s64(words, f, z0, z1, shell_scratch, state, st)
                             : jfa_early_launch(words, f, z0, z1, shell_scratch, state, st);
 }
+bool early_takes(const Frame& f) { return (jfa_state64(f.n) ? jfa_early_supported_s64(f) : jfa_early_supported(f)) != 0; }
 int pass_any(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f, uint32_t z0,
              uint32_t z1, uint32_t k, const uint32_t* words, float* sdf, uint32_t* seeds, cudaStream_t st) {
     return jfa_state64(f.n) ? jfa_pass_launch_s64(below, mid, above, dst, f, z0, z1, k, words, sdf, seeds, st)
@@ -121,14 +125,15 @@ struct HostSink {
 // Runs seed extraction + all passes + signed output on one GPU.  sdf may be NULL: the final pass never writes its
 // state destination, so the signed distance then goes INTO that free state buffer (4 B/voxel of HBM saved; at 2048^3
 // that is what makes the job fit one GPU) and *sdf_at tells the caller where it is.
+// shell_ready: the seed-shell bits of `words` are already in sb (the fused CSG + shell kernel wrote them).
 int jfa_run(const uint32_t* words, const Frame& f, uint32_t* sa, uint32_t* sb, float* sdf, uint32_t* seeds, cudaStream_t st,
-            float** sdf_at = nullptr, const HostSink* sink = nullptr) {
+            float** sdf_at = nullptr, const HostSink* sink = nullptr, bool shell_ready = false) {
     const uint32_t n = f.n;
     // seed extraction + the passes k = N/2, N/4, N/8 fused (jfa_early.cu; the shell bits go through the free buffer sb),
     // or, for shapes it does not take, seed extraction and every pass on its own
     uint32_t k_first = n / 2;
     {
-        const int rc = early_any(words, f, 0, n, sb, sa, st);
+        const int rc = early_any(words, f, 0, n, sb, sa, st, shell_ready);
         if (rc < 0) return rc;
         if (rc == 0) k_first = n / 16;
         else VPB_TRY(seed_any(words, n, 0, n, sa, st));
@@ -226,7 +231,7 @@ static int create_resources() {
 static void release_resources() {
     if (g_ctx.stream) cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
-    for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.scratch, &g_ctx.state_a,
+    for (Buf* b : {&g_ctx.verts, &g_ctx.tris, &g_ctx.grid_a, &g_ctx.grid_b, &g_ctx.grid_c, &g_ctx.scratch, &g_ctx.state_a,
                    &g_ctx.state_b, &g_ctx.sdf, &g_ctx.seeds, &g_ctx.slot_words[0], &g_ctx.slot_words[1], &g_ctx.slot_sdf[0],
                    &g_ctx.slot_sdf[1]})
         b->release();
@@ -356,6 +361,11 @@ int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell, void* stre
     return shell_launch(words, n, shell, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
+int vpb_csg_shell_dev(const uint32_t* a, const uint32_t* b, uint32_t n, int op, uint32_t* result, uint32_t* shell, void* stream) {
+    VPB_TRY(require_ready());
+    return csg_shell_launch(a, b, n, op, result, shell, stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
 size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1) {
     if (z1 <= z0 || z1 > n) return 0;
     return (size_t)n * n * (z1 - z0) * state_size(n);
@@ -379,6 +389,15 @@ int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint3
     VPB_REQUIRE(n > 0 && n <= kMaxJfaN && z0 < z1 && z1 <= n, "jfa_early: bad n=%u slab [%u,%u)", n, z0, z1);
     return early_any(words_full, make_frame(n, vs, origin), z0, z1, shell_scratch, state,
                      stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
+}
+
+int vpb_jfa_early_from_shell_dev(const uint32_t* shell, uint32_t n, uint32_t z0, uint32_t z1, float vs, const float origin[3],
+                                 uint32_t* state, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && shell && state, "jfa_early_from_shell: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && z0 < z1 && z1 <= n, "jfa_early_from_shell: bad n=%u slab [%u,%u)", n, z0, z1);
+    return early_any(nullptr, make_frame(n, vs, origin), z0, z1, const_cast<uint32_t*>(shell), state,
+                     stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, true);
 }
 
 int vpb_jfa_early_dist_dev(const uint32_t* words_full, uint32_t n, float vs, const float origin[3], uint32_t rz_lo,
@@ -554,6 +573,39 @@ int vpb_jfa_host(const uint32_t* words, uint32_t n, float vs, const float origin
     return finish_timing();
 }
 
+// Voxelizes every mesh in the shared frame and folds grids[0] = op(grids[0], grids[i]) (apps/cli/main.cpp:92-186); the
+// folded grid ends up in `final_dst`.  With `shell_dst`, the LAST fold also writes the seed shell of the result there
+// (csg_shell_launch: CSG fused with the seed extraction) and *shell_ready tells; `acc` is then the accumulator of the fold
+// (it must differ from final_dst), otherwise everything happens in final_dst.
+static int occupancy_stage(int n_meshes, const float* const* verts, const uint64_t* n_verts, const uint32_t* const* tris,
+                           const uint64_t* n_tris, const Frame& f, int op, uint32_t* final_dst, uint32_t* acc, uint32_t* operand,
+                           uint32_t* shell_dst, bool* shell_ready, cudaEvent_t first_upload_done, cudaStream_t st) {
+    const uint64_t nw = grid_words(f.n);
+    const bool fuse = shell_dst && acc && n_meshes >= 2 && op != VPB_OP_VOID && f.n % 32u == 0 && early_takes(f);
+    *shell_ready = false;
+    uint32_t* a = fuse ? acc : final_dst;
+    for (int i = 0; i < n_meshes; ++i) {
+        VPB_TRY(upload_mesh(verts[i], n_verts[i], tris[i], n_tris[i], st));
+        if (i == 0 && first_upload_done) VPB_CUDA(cudaEventRecord(first_upload_done, st));
+        uint32_t* target = i == 0 ? a : operand;
+        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts[i], g_ctx.tris.as<uint32_t>(), n_tris[i], f, 0, f.n, target,
+                           g_ctx.scratch.p, g_ctx.scratch.cap, st));
+        if (i == 0 || op == VPB_OP_VOID) continue;
+        if (fuse && i == n_meshes - 1) {
+            const int rc = csg_shell_launch(a, operand, f.n, op, final_dst, shell_dst, st);
+            if (rc < 0) return rc;
+            *shell_ready = rc == 0;
+            if (rc != 0) {                                   // not taken after all: fold in place and move the result
+                VPB_TRY(csg_launch(a, operand, nw, op, st));
+                VPB_CUDA(cudaMemcpyAsync(final_dst, a, nw * 4, cudaMemcpyDeviceToDevice, st));
+            }
+        } else {
+            VPB_TRY(csg_launch(a, operand, nw, op, st));
+        }
+    }
+    return VPB_OK;
+}
+
 int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n_verts, const uint32_t* const* tris,
                       const uint64_t* n_tris, uint32_t n, float vs, const float origin[3], int op, uint32_t* words_out,
                       float* sdf_out) {
@@ -573,23 +625,20 @@ int vpb_pipeline_host(int n_meshes, const float* const* verts, const uint64_t* n
     if (sdf_out) VPB_TRY(reserve_jfa(n, false));
     // H2D of mesh i and its kernels are interleaved on one stream; ev[0..1] bracket the first upload only,
     // the rest is accounted to "kernels" (there is a single timeline).
+    const bool want_fuse = sdf_out && n_meshes >= 2 && op != VPB_OP_VOID && n % 32u == 0;
+    if (want_fuse) VPB_TRY(g_ctx.grid_c.reserve(nw * 4 + 16));
     VPB_CUDA(cudaEventRecord(g_ctx.ev[0], st));
-    for (int i = 0; i < n_meshes; ++i) {
-        VPB_TRY(upload_mesh(verts[i], n_verts[i], tris[i], n_tris[i], st));
-        if (i == 0) VPB_CUDA(cudaEventRecord(g_ctx.ev[1], st));
-        uint32_t* target = i == 0 ? g_ctx.grid_a.as<uint32_t>() : g_ctx.grid_b.as<uint32_t>();
-        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts[i], g_ctx.tris.as<uint32_t>(), n_tris[i], f, 0, n, target,
-                           g_ctx.scratch.p, g_ctx.scratch.cap, st));
-        // apps/cli/main.cpp:126-186: fold into grids[0] for i > 0 when an operator is selected
-        if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(g_ctx.grid_a.as<uint32_t>(), g_ctx.grid_b.as<uint32_t>(), nw, op, st));
-    }
+    bool shell_ready = false;
+    VPB_TRY(occupancy_stage(n_meshes, verts, n_verts, tris, n_tris, f, op, g_ctx.grid_a.as<uint32_t>(),
+                            want_fuse ? g_ctx.grid_c.as<uint32_t>() : nullptr, g_ctx.grid_b.as<uint32_t>(),
+                            want_fuse ? g_ctx.state_b.as<uint32_t>() : nullptr, &shell_ready, g_ctx.ev[1], st));
     float* sdf_dev = nullptr;
     const bool chunked = sdf_out && sink_takes(n);
     if (sdf_out) {
         HostSink sink;
         sink.sdf_host = sdf_out; sink.kernels_done = g_ctx.ev[2];
         VPB_TRY(jfa_run(g_ctx.grid_a.as<uint32_t>(), f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(),
-                        nullptr, nullptr, st, &sdf_dev, chunked ? &sink : nullptr));
+                        nullptr, nullptr, st, &sdf_dev, chunked ? &sink : nullptr, shell_ready));
     }
     if (!chunked) VPB_CUDA(cudaEventRecord(g_ctx.ev[2], st));
     if (words_out) VPB_CUDA(cudaMemcpyAsync(words_out, g_ctx.grid_a.p, nw * 4, cudaMemcpyDeviceToHost, st));
@@ -628,13 +677,9 @@ int vpb_pipeline_submit(int n_meshes, const float* const* verts, const uint64_t*
         VPB_TRY(g_ctx.slot_sdf[slot].reserve(vox * 4));
     }
     uint32_t* words = g_ctx.slot_words[slot].as<uint32_t>();          // grids[0] of this job lives in the slot
-    for (int i = 0; i < n_meshes; ++i) {
-        VPB_TRY(upload_mesh(verts[i], n_verts[i], tris[i], n_tris[i], st));
-        uint32_t* target = i == 0 ? words : g_ctx.grid_b.as<uint32_t>();
-        VPB_TRY(vox_launch(g_ctx.verts.as<float>(), n_verts[i], g_ctx.tris.as<uint32_t>(), n_tris[i], f, 0, n, target,
-                           g_ctx.scratch.p, g_ctx.scratch.cap, st));
-        if (i > 0 && op != VPB_OP_VOID) VPB_TRY(csg_launch(words, g_ctx.grid_b.as<uint32_t>(), nw, op, st));
-    }
+    bool shell_ready = false;
+    VPB_TRY(occupancy_stage(n_meshes, verts, n_verts, tris, n_tris, f, op, words, g_ctx.grid_a.as<uint32_t>(),
+                            g_ctx.grid_b.as<uint32_t>(), sdf_out ? g_ctx.state_b.as<uint32_t>() : nullptr, &shell_ready, nullptr, st));
     VPB_CUDA(cudaEventRecord(g_ctx.chunk_ev[15], st));                 // occupancy final
     bool copies_recorded = false;
     if (sdf_out) {
@@ -647,7 +692,7 @@ int vpb_pipeline_submit(int n_meshes, const float* const* verts, const uint64_t*
             VPB_CUDA(cudaMemcpyAsync(words_out, words, nw * 4, cudaMemcpyDeviceToHost, cs));
         }
         VPB_TRY(jfa_run(words, f, g_ctx.state_a.as<uint32_t>(), g_ctx.state_b.as<uint32_t>(), g_ctx.slot_sdf[slot].as<float>(),
-                        nullptr, st, nullptr, chunked ? &sink : nullptr));
+                        nullptr, st, nullptr, chunked ? &sink : nullptr, shell_ready));
         copies_recorded = chunked;
         if (!chunked) {
             VPB_CUDA(cudaEventRecord(g_ctx.chunk_ev[14], st));

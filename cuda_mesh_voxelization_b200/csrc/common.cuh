@@ -138,6 +138,7 @@ int vox_surface_launch(const float* verts, uint64_t n_verts, const uint32_t* tri
                        uint32_t z0, uint32_t z1, uint32_t* words_slab, void* scratch, size_t scratch_bytes, cudaStream_t st);
 int csg_launch(uint32_t* a, const uint32_t* b, uint64_t n_words, int op, cudaStream_t st);
 int shell_launch(const uint32_t* words, uint32_t n, uint32_t* shell, cudaStream_t st);
+int csg_shell_launch(const uint32_t* a, const uint32_t* b, uint32_t n, int op, uint32_t* c, uint32_t* shell, cudaStream_t st);
 int jfa_seed_launch(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_pass_launch(const uint32_t* below, const uint32_t* mid, const uint32_t* above, uint32_t* dst, const Frame& f,
                     uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full, float* sdf, uint32_t* seeds,
@@ -150,6 +151,9 @@ int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint
 // seed extraction + the passes k = N/2, N/4, N/8 in one kernel (jfa_early.cu); 1 = shape/frame not taken, caller runs them one by one
 int jfa_early_launch(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
                      uint32_t* state, cudaStream_t st);
+// the same with the seed-shell bits already in `shell` (csg_shell_launch wrote them): no shell kernel
+int jfa_early_from_shell_launch(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
+int jfa_early_from_shell_launch_s64(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_early_supported(const Frame& f);
 int jfa_early_supported_s64(const Frame& f);
 int jfa_early_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,

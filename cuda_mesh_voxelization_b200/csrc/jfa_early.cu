@@ -343,14 +343,14 @@ int VPB_SFX(jfa_early_supported)(const Frame& f) {
 // shell_scratch receives the seed-shell bits (ceil(N^3/32) words).
 // Returns 1 when the shape/frame is not one this kernel takes (the caller then runs seed extraction + the ordinary
 // passes), VPB_OK when launched.  VPB_JFA_EARLY=0 turns it off (A/B timing; parity tests of the ordinary passes).
-int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
-                              uint32_t* state_, cudaStream_t st) {
+static int early_launch_impl(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
+                             uint32_t* state_, bool shell_ready, cudaStream_t st) {
     const uint32_t n = f.n;
     EarlyArgs a;
     if (!early_supported(f, &a.key_base) || z0 >= z1 || z1 > n) return 1;
     if ((reinterpret_cast<uintptr_t>(state_) & 15u) != 0) return 1;
-    VPB_REQUIRE(words_full && shell_scratch && state_, "jfa_early: null buffer");
-    { const int rc = shell_launch(words_full, n, shell_scratch, st); if (rc != VPB_OK) return rc; }
+    VPB_REQUIRE((words_full || shell_ready) && shell_scratch && state_, "jfa_early: null buffer");
+    if (!shell_ready) { const int rc = shell_launch(words_full, n, shell_scratch, st); if (rc != VPB_OK) return rc; }
     a.K = n / 8u;
     a.shell = shell_scratch;
     a.dst = reinterpret_cast<state_t*>(state_);
@@ -362,6 +362,15 @@ int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32
     const char* env = getenv("VPB_JFA_EARLY");
     const bool g16 = env && strcmp(env, "16") == 0 && a.K % 16u == 0;
     return g16 ? launch<16, 512>(a, a.K, st) : launch<8, 256>(a, a.K, st);
+}
+
+int VPB_SFX(jfa_early_launch)(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
+                              uint32_t* state_, cudaStream_t st) {
+    return early_launch_impl(words_full, f, z0, z1, shell_scratch, state_, false, st);
+}
+int VPB_SFX(jfa_early_from_shell_launch)(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state_,
+                                         cudaStream_t st) {
+    return early_launch_impl(nullptr, f, z0, z1, const_cast<uint32_t*>(shell), state_, true, st);
 }
 
 // Multi-GPU, work-sharing form: this rank runs only the lattices with z residue in [rz_lo, rz_hi) -- all of their planes --

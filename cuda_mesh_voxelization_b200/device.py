@@ -68,6 +68,7 @@ class DevicePipeline:
         i32 = dict(dtype=torch.int32, device=self.device)
         self.grid_a = torch.empty(nw, **i32)
         self.grid_b = torch.empty(nw, **i32)
+        self.grid_c = None                    # accumulator of the fold when its last step is fused with the seed shell
         self.state_bytes = int(self.lib.vpb_jfa_state_bytes(self.n, 0, self.n))
         self.state_a = torch.empty(self.state_bytes // 4, **i32)
         self.state_b = torch.empty(self.state_bytes // 4, **i32)
@@ -98,7 +99,21 @@ class DevicePipeline:
     def csg(self, op):
         capi.check(self.lib.vpb_csg_dev(_ptr(self.grid_a), _ptr(self.grid_b), self.grid_a.numel(), op, _stream()))
 
-    def jfa(self, record_passes=False):
+    def csg_shell(self, op) -> bool:
+        """Last fold of the pipeline fused with the seed-shell extraction (vpb_csg_shell_dev): grid_a op grid_b -> the new
+        grid_a, its seed shell -> state_a (where jfa() expects it).  False when the library does not take the shape."""
+        if self.grid_c is None:
+            self.grid_c = torch.empty_like(self.grid_a)
+        rc = self.lib.vpb_csg_shell_dev(_ptr(self.grid_a), _ptr(self.grid_b), self.n, op, _ptr(self.grid_c), _ptr(self.state_a),
+                                        _stream())
+        if rc < 0:
+            capi.check(rc)
+        if rc != 0:
+            return False
+        self.grid_a, self.grid_c = self.grid_c, self.grid_a
+        return True
+
+    def jfa(self, record_passes=False, shell_ready=False):
         n, st = self.n, _stream()
         # seed extraction + the passes k = N/2, N/4, N/8 in one kernel where the library takes the grid (the result lands
         # in state_b, where three ping-pong passes would have left it; state_a is the scratch of the shell bits)
@@ -106,8 +121,13 @@ class DevicePipeline:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        rc = self.lib.vpb_jfa_early_dev(_ptr(self.grid_a), n, 0, n, self.vs, self._o(), _ptr(self.state_a),
-                                        _ptr(self.state_b), st) if n >= 16 else 1
+        if shell_ready:
+            rc = self.lib.vpb_jfa_early_from_shell_dev(_ptr(self.state_a), n, 0, n, self.vs, self._o(), _ptr(self.state_b), st)
+            if rc != 0:
+                capi.check(rc if rc < 0 else -1)
+        else:
+            rc = self.lib.vpb_jfa_early_dev(_ptr(self.grid_a), n, 0, n, self.vs, self._o(), _ptr(self.state_a),
+                                            _ptr(self.state_b), st) if n >= 16 else 1
         if rc < 0:
             capi.check(rc)
         if record_passes and rc == 0:
@@ -149,12 +169,20 @@ class DevicePipeline:
 
     def run(self, meshes, op=capi.OP_VOID, sdf=True, record_passes=False):
         """The CLI loop (apps/cli/main.cpp:92-218) without leaving the device."""
+        # the last fold is fused with the seed extraction when a signed distance field follows and the fused early kernel
+        # takes the frame (it reads the shell bits the fused CSG kernel leaves in state_a)
+        fuse = (sdf and len(meshes) >= 2 and op != capi.OP_VOID and self.n % 32 == 0 and self.n >= 16 and
+                bool(self.lib.vpb_jfa_early_supported(self.n, self.vs, self._o())))
+        shell_ready = False
         for i, m in enumerate(meshes):
             self.voxelize(m, self.grid_a if i == 0 else self.grid_b)
             if i > 0 and op != capi.OP_VOID:
-                self.csg(op)
+                if fuse and i == len(meshes) - 1 and self.csg_shell(op):
+                    shell_ready = True
+                else:
+                    self.csg(op)
         if sdf:
-            self.jfa(record_passes)
+            self.jfa(record_passes, shell_ready=shell_ready)
 
     def words_host(self) -> np.ndarray:
         return self.grid_a.cpu().numpy().view(np.uint32)

@@ -126,6 +126,12 @@ VPB_API int vpb_voxelize_surface_dev(const float* verts_xyz, uint64_t n_verts, c
 VPB_API int vpb_csg_dev(uint32_t* a_inout, const uint32_t* b, uint64_t n_words, int op, void* stream);
 /* shell_out = seed shell of `words` (full N^3 grid), both dense bit grids. */
 VPB_API int vpb_shell_dev(const uint32_t* words, uint32_t n, uint32_t* shell_out, void* stream);
+/* CSG fused with seed extraction: result_out = a op b AND shell_out = seed shell of that result, in one pass over both
+ * operands (full N^3 grids; result_out and shell_out must not alias a or b).  Replaces CSG::Compute (vplib/src/csg/csg.h:35-36)
+ * followed by the init phase of JFA::Compute (vplib/src/jfa/sequential.cpp:24-63) for the last fold of a pipeline; continue
+ * with vpb_jfa_early_from_shell_dev.  Returns 0, or 1 when the shape is not taken (N % 32 != 0: use vpb_csg_dev). */
+VPB_API int vpb_csg_shell_dev(const uint32_t* a, const uint32_t* b, uint32_t n, int op, uint32_t* result_out,
+                              uint32_t* shell_out, void* stream);
 
 /* JFA state: one 32-bit word per voxel (packed nearest-seed coordinates, 0 = none), N <= 1024. */
 VPB_API size_t vpb_jfa_state_bytes(uint32_t n, uint32_t z0, uint32_t z1);
@@ -142,6 +148,9 @@ VPB_API int vpb_jfa_seed_dev(const uint32_t* words_full, uint32_t n, uint32_t z0
 VPB_API int vpb_jfa_early_supported(uint32_t n, float voxel_size, const float origin[3]);
 VPB_API int vpb_jfa_early_dev(const uint32_t* words_full, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
                               const float origin[3], uint32_t* shell_scratch, uint32_t* state_slab, void* stream);
+/* The same when the seed-shell bits of the full grid are already in `shell` (vpb_csg_shell_dev / vpb_shell_dev). */
+VPB_API int vpb_jfa_early_from_shell_dev(const uint32_t* shell, uint32_t n, uint32_t z0, uint32_t z1, float voxel_size,
+                                         const float origin[3], uint32_t* state_slab, void* stream);
 /* The same kernel, work-sharing form for multi-GPU runs whose result slabs are mapped into every process (symmetric
  * memory over NVLink): the caller runs only the lattices with z residue (z mod N/8) in [rz_lo, rz_hi) -- all eight planes of
  * each -- and plane z is stored into slab_states[z / slab_planes] (r < world <= 8; slab_planes * world == N; addresses valid

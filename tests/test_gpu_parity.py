@@ -614,3 +614,32 @@ def test_config4_10m_faces_surface_and_solid_1024_with_slabs(meshes, oracle, vpb
                                         ctypes.c_void_p(scratch.data_ptr()), scratch.numel(), None))
     torch.cuda.synchronize()
     assert np.array_equal(full.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("n", [32, 64, 96])
+def test_csg_fused_with_seed_shell(n, oracle, vpb):
+    """vpb_csg_shell_dev (CSG fused with the seed extraction, north_star): result == CSG::Compute's, shell == the seed shell
+    of that result (vplib/src/csg/sequential.cpp:18-27, jfa/sequential.cpp:36-60), for every operator, on random grids with
+    set voxels on every face of the grid."""
+    import ctypes
+    import torch
+    rng = np.random.default_rng(100 + n)
+    nw = n ** 3 // 32
+    a = rng.integers(0, 2 ** 32, nw, dtype=np.uint32) | rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
+    b = rng.integers(0, 2 ** 32, nw, dtype=np.uint32) & rng.integers(0, 2 ** 32, nw, dtype=np.uint32)
+    ta = torch.from_numpy(a.view(np.int32)).cuda()
+    tb = torch.from_numpy(b.view(np.int32)).cuda()
+    lib = vpb.load()
+    for op in (1, 2, 3):
+        tc = torch.empty_like(ta)
+        ts = torch.empty_like(ta)
+        rc = lib.vpb_csg_shell_dev(ctypes.c_void_p(ta.data_ptr()), ctypes.c_void_p(tb.data_ptr()), n, op,
+                                   ctypes.c_void_p(tc.data_ptr()), ctypes.c_void_p(ts.data_ptr()), ctypes.c_void_p(1))
+        assert rc == 0
+        torch.cuda.synchronize()
+        want = oracle.csg(a, b, n, op)
+        assert np.array_equal(tc.cpu().numpy().view(np.uint32), want)
+        assert np.array_equal(ts.cpu().numpy().view(np.uint32), oracle.seed_shell(want, n))
+    # a shape the fused kernel does not take
+    assert lib.vpb_csg_shell_dev(ctypes.c_void_p(ta.data_ptr()), ctypes.c_void_p(tb.data_ptr()), 33, 1,
+                                 ctypes.c_void_p(tc.data_ptr()), ctypes.c_void_p(ts.data_ptr()), ctypes.c_void_p(1)) == 1
