@@ -332,9 +332,17 @@ def run_ours(args):
     ms_total = float(ms.item())
     launches = capi.kernel_launches() - launches0
 
+    if world > 1 and getattr(pipe, "trace", None):
+        # VPB_SPLIT_TRACE=1: where the parity-split passes of the LAST step wait (per launch: flag wait, kernel), per rank
+        tr = pipe.trace[-2 * (len(pipe.steps) - 1):]
+        line = " ".join(f"k{k}q{q}:w{a.elapsed_time(b):.2f}+{b.elapsed_time(c):.2f}" for k, q, a, b, c in tr)
+        print(f"[trace rank {rank}] {line}", file=sys.stderr, flush=True)
     partition_label = None
     if world > 1 and not replicas:
-        halo = {"push": "halo planes written into the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
+        halo = {"split": "every pass runs as two half-slab launches; when a half is done copy engines write its boundary planes "
+                         "into the neighbour's symmetric-memory halo over NVLink and raise a flag there, the half that needs them "
+                         "waits for the flag on the device: the exchange of pass i+1 hides behind pass i, no barriers",
+                "push": "halo planes written into the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
                         "device-side barrier per pass",
                 "pull": "halo planes read from the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
                         "device-side barrier per pass"}.get(pipe.dma, "NCCL send/recv halo exchange per pass")

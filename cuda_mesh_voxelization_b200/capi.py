@@ -46,6 +46,13 @@ SIGNATURES = [
     ("vpb_csg_shell_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp]),
     ("vpb_jfa_early_from_shell_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, _f32p,
                                                     _vp, _vp]),
+    ("vpb_jfa_pass_part_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_float, _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    ("vpb_copy_planes_dev", ctypes.c_int, [_vp, ctypes.c_size_t, _vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _vp]),
+    ("vpb_jfa_early_cyclic_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp,
+                                                _vp, _vp]),
+    ("vpb_jfa_pass_cyclic_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                               ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, _f32p, _vp]),
     ("vpb_jfa_state_bytes", ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     ("vpb_jfa_seed_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp]),
     ("vpb_jfa_early_supported", ctypes.c_int, [ctypes.c_uint32, ctypes.c_float, _f32p]),

@@ -421,6 +421,50 @@ int vpb_jfa_pass_dev(const uint32_t* below, const uint32_t* mid, const uint32_t*
                     stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream);
 }
 
+int vpb_jfa_pass_part_dev(const uint32_t* src_mid, uint32_t* dst, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float vs,
+                          const float origin[3], uint32_t res_step, uint32_t res_off, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && src_mid && dst, "jfa_pass_part: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && z0 < z1 && z1 <= n && k >= 1 && k < n, "jfa_pass_part: bad n=%u slab [%u,%u) k=%u", n, z0, z1, k);
+    if (jfa_state64(n)) return 1;
+    return jfa_pass_flood5_launch(src_mid, dst, make_frame(n, vs, origin), z0, z1, k, nullptr, nullptr, nullptr,
+                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, res_step, res_off, 1, 0);
+}
+
+int vpb_copy_planes_dev(void* dst, size_t dst_stride, const void* src, size_t src_stride, size_t plane_bytes, size_t n_planes,
+                        void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(dst && src && plane_bytes > 0 && dst_stride >= plane_bytes && src_stride >= plane_bytes, "copy_planes: bad argument");
+    if (n_planes == 0) return VPB_OK;
+    VPB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, src, src_stride, plane_bytes, n_planes, cudaMemcpyDeviceToDevice,
+                               stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream));
+    return VPB_OK;
+}
+
+int vpb_jfa_early_cyclic_dev(const uint32_t* words_full, uint32_t n, float vs, const float origin[3], uint32_t world, uint32_t rank,
+                             uint32_t* shell_scratch, uint32_t* state_cyclic, void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && words_full && shell_scratch && state_cyclic, "jfa_early_cyclic: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && world >= 1 && rank < world, "jfa_early_cyclic: bad n=%u rank %u of %u", n, rank, world);
+    const Frame f = make_frame(n, vs, origin);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
+    return jfa_state64(n) ? jfa_early_cyclic_launch_s64(words_full, f, world, rank, shell_scratch, state_cyclic, st)
+                          : jfa_early_cyclic_launch(words_full, f, world, rank, shell_scratch, state_cyclic, st);
+}
+
+int vpb_jfa_pass_cyclic_dev(const uint32_t* src, uint32_t* dst, uint32_t n, uint32_t world, uint32_t rank, uint32_t k,
+                            uint32_t plane_lo, uint32_t plane_hi, float vs, const float origin[3], void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && src && dst, "jfa_pass_cyclic: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && world >= 1 && rank < world && n % world == 0 && k >= 1 && k < n,
+                "jfa_pass_cyclic: bad n=%u rank %u of %u k=%u", n, rank, world, k);
+    VPB_REQUIRE(plane_lo < plane_hi && plane_hi <= n / world, "jfa_pass_cyclic: bad plane range [%u,%u) of %u", plane_lo, plane_hi, n / world);
+    if (jfa_state64(n) || k % world != 0) return 1;
+    const size_t off = (size_t)plane_lo * n * n;
+    return jfa_pass_flood5_launch(src + off, dst + off, make_frame(n, vs, origin), plane_lo, plane_hi, k, nullptr, nullptr, nullptr,
+                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, 1, 0, world, rank);
+}
+
 int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes, uint32_t* dst,
                           uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float vs, const float origin[3],
                           const uint32_t* words_full, float* sdf, uint32_t* seeds, void* stream) {

@@ -148,12 +148,22 @@ int jfa_pass_flood_peer_launch(const uint32_t* const* slabs, uint32_t world, uin
                                float* sdf, uint32_t* seeds, cudaStream_t st);
 int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint32_t z1, const uint32_t* words_full,
                         float* sdf, uint32_t* seeds, cudaStream_t st);
+// flood pass v5 (jfa_flood5.cu): 32-bit state, source planes contiguous around the slab; optionally only the output planes
+// zl with zl % res_step == res_off.  1 = shape not taken.
+int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k,
+                           const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t res_step,
+                           uint32_t res_off, uint32_t zmul, uint32_t zadd);
 // seed extraction + the passes k = N/2, N/4, N/8 in one kernel (jfa_early.cu); 1 = shape/frame not taken, caller runs them one by one
 int jfa_early_launch(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
                      uint32_t* state, cudaStream_t st);
 // the same with the seed-shell bits already in `shell` (csg_shell_launch wrote them): no shell kernel
 int jfa_early_from_shell_launch(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_early_from_shell_launch_s64(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
+// z-cyclic multi-GPU form: rank's planes z = rank (mod world) as a dense buffer (jfa_early.cu)
+int jfa_early_cyclic_launch(const uint32_t* words_full, const Frame& f, uint32_t world, uint32_t rank, uint32_t* shell_scratch,
+                            uint32_t* state, cudaStream_t st);
+int jfa_early_cyclic_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t world, uint32_t rank, uint32_t* shell_scratch,
+                                uint32_t* state, cudaStream_t st);
 int jfa_early_supported(const Frame& f);
 int jfa_early_supported_s64(const Frame& f);
 int jfa_early_launch_s64(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,

@@ -55,6 +55,10 @@ struct EarlyArgs {
     // owners' buffers mapped over NVLink); z0 = 0, z1 = n
     uint32_t rz0, T;
     state_t* dst_rank[8];
+    // z-cyclic mode (cyc != 0; T == 0): the launch runs the z residues rz0 + i * rz_step and stores plane z at plane z / cyc of
+    // dst -- the layout in which rank r of cyc owns the planes z = r (mod cyc).  K is a multiple of cyc, so every plane of a
+    // lattice with z residue = r (mod cyc) belongs to rank r: with rz0 = r, rz_step = cyc all stores are local
+    uint32_t rz_step, cyc;
 };
 
 __device__ __forceinline__ float sqdiff(float s, float q) {
@@ -105,7 +109,7 @@ jfa_early(const EarlyArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = a.n, K = a.K;
-    const uint32_t rx0 = blockIdx.x * G, ry = blockIdx.y, rz = blockIdx.z + a.rz0;
+    const uint32_t rx0 = blockIdx.x * G, ry = blockIdx.y, rz = blockIdx.z * a.rz_step + a.rz0;
     const float* __restrict__ lut = a.lut;
     // Slab runs only need the lattice planes l with rz + l K in [z0, z1) at the end.  The pass with lattice stride S
     // reads sources S planes away, so its targets are needed on [lo1 - (S - 1), hi1 + (S - 1)] (S = 1, 2, 4: margins 0,
@@ -269,6 +273,8 @@ jfa_early(const EarlyArgs a) {
 #pragma unroll
             for (uint32_t r = 1; r < 8; ++r) base = owner == r ? a.dst_rank[r] : base;
             st4(base + ((size_t)(z - owner * a.T) * n + y) * n + x, v);                  // 7 of 8 planes: a store over NVLink
+        } else if (a.cyc) {
+            st4(a.dst + ((size_t)(z / a.cyc) * n + y) * n + x, v);
         } else {
             st4(a.dst + ((size_t)(z - a.z0) * n + y) * n + x, v);
         }
@@ -355,7 +361,7 @@ static int early_launch_impl(const uint32_t* words_full, const Frame& f, uint32_
     a.shell = shell_scratch;
     a.dst = reinterpret_cast<state_t*>(state_);
     a.n = n; a.z0 = z0; a.z1 = z1;
-    a.rz0 = 0; a.T = 0;
+    a.rz0 = 0; a.T = 0; a.rz_step = 1; a.cyc = 0;
     for (auto& d : a.dst_rank) d = nullptr;
     a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
@@ -395,10 +401,33 @@ int VPB_SFX(jfa_early_dist_launch)(const uint32_t* words_full, const Frame& f, u
     a.shell = shell_scratch;
     a.dst = nullptr;
     a.n = n; a.z0 = 0; a.z1 = n;
-    a.rz0 = rz_lo; a.T = slab_planes;
+    a.rz0 = rz_lo; a.T = slab_planes; a.rz_step = 1; a.cyc = 0;
     a.lut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.lut) return VPB_ERR_CUDA;
     return launch<8, 256>(a, rz_hi - rz_lo, st);
+}
+
+// Multi-GPU, z-cyclic form: rank `rank` of `world` owns the planes z = rank (mod world) and keeps them as a dense buffer of
+// N / world planes (plane z at index z / world).  It runs exactly the lattices whose z residue is = rank (mod world) -- all
+// eight planes of such a lattice are its own, K = N/8 being a multiple of world -- so the work is shared world ways like in
+// the work-sharing form above, but every store is local.  Same return convention as jfa_early_launch.
+int VPB_SFX(jfa_early_cyclic_launch)(const uint32_t* words_full, const Frame& f, uint32_t world, uint32_t rank,
+                                     uint32_t* shell_scratch, uint32_t* state_, cudaStream_t st) {
+    const uint32_t n = f.n;
+    EarlyArgs a;
+    if (!early_supported(f, &a.key_base)) return 1;
+    a.K = n / 8u;
+    if (world == 0 || a.K % world != 0 || (reinterpret_cast<uintptr_t>(state_) & 15u) != 0) return 1;
+    VPB_REQUIRE(words_full && shell_scratch && state_ && rank < world, "jfa_early_cyclic: bad argument");
+    { const int rc = shell_launch(words_full, n, shell_scratch, st); if (rc != VPB_OK) return rc; }
+    a.shell = shell_scratch;
+    a.dst = reinterpret_cast<state_t*>(state_);
+    a.n = n; a.z0 = 0; a.z1 = n;
+    a.rz0 = rank; a.rz_step = world; a.T = 0; a.cyc = world;
+    for (int r = 0; r < 8; ++r) a.dst_rank[r] = nullptr;
+    a.lut = VPB_SFX(jfa_lut_launch)(f, st);
+    if (!a.lut) return VPB_ERR_CUDA;
+    return launch<8, 256>(a, a.K / world, st);
 }
 
 }  // namespace vpb

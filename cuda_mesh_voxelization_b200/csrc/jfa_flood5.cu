@@ -53,10 +53,14 @@ struct F5Args {
     uint32_t* seeds;          // FINAL only, optional
     const float* glut;        // px | py | pz, 3 * MAXN floats
     uint32_t n, z0, T;
-    int k;
+    int k;                    // step of the pass in voxels (x, y; and z unless the planes are z-cyclic)
+    int kz;                   // the same step in PLANES of the source / destination buffers (k, or k / zmul)
+    int zmul, zadd;           // grid z of buffer plane zl (slab-local) = (zl + z0) * zmul + zadd   (1, 0 for a z-slab)
+    int zn;                   // (zl + z0) in [0, zn) <=> the plane is inside the grid
     int zbias;                // tensor-map z coordinate of slab-local plane 0
     int lz, segs_z;           // outputs per march segment, segments per z-lattice column
-    int res_z, cols;          // z residues (= z-lattice columns) in the slab; consecutive columns walked by one CTA
+    int res_z, cols;          // z-lattice columns this launch walks; consecutive columns walked by one CTA
+    int rz_step, rz_off;      // column i is the z residue i * rz_step + rz_off (1, 0: all of them; see jfa_pass_flood5_launch)
     int tiles_y;              // TR-row tiles per y-lattice column
     uint32_t key_base;        // FINAL: (key >> 4) + key_base are the bits of the (unscaled) distance
     float scale;              // power of two the world coordinates are multiplied with inside the kernel (see KEY_E0)
@@ -155,7 +159,7 @@ struct Flood5 {
         // ring-entry offset of the candidate with in-plane code: 0 = the voxel's own entry (row 1, column 1),
         // 1 + r*4 + c = row r, column c
         __shared__ uint32_t s_dec[16];
-        const int n = (int)a.n, k = a.k;
+        const int n = (int)a.n, k = a.k, kz = a.kz;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (threadIdx.x < 16) {
             const uint32_t cc = threadIdx.x == 0 ? 5u : threadIdx.x - 1u;
@@ -203,7 +207,7 @@ struct Flood5 {
         const vox_t plane_sz = (vox_t)n * (vox_t)n;
         uint32_t phases = 0;                                       // parity each ring slot's barrier completes next
 
-        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
+        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * kz + (int)a.z0; return gz >= 0 && gz < a.zn; };
         // plane p of the march -> ring slot (p + 1) & 3, by the copy engine.  Called by everyone right after a CTA barrier
         // that follows the last read of the slot's previous plane (p - 4); one thread arms the barrier and issues the boxes.
         auto fetch = [&](int p) {
@@ -211,7 +215,7 @@ struct Flood5 {
                 const int slot = (p + 1) & 3;
                 const uint32_t bar = bar_s + 8u * (uint32_t)slot;
                 const uint32_t dst = ring_s + (uint32_t)(slot * C::SLOT * 4);
-                const int tz = zl0 + p * k + a.zbias;
+                const int tz = zl0 + p * kz + a.zbias;
                 mbar_expect_tx(bar, (uint32_t)C::PW * 4u);
                 if (C::SEGS) {
 #pragma unroll
@@ -298,7 +302,7 @@ struct Flood5 {
                 for (int r2 = 0; r2 < RPT; ++r2) {
                     wpre[r2] = 0u;
                     if (!ok[r2]) continue;
-                    const vox_t bit = (vox_t)(zl0 + (p - 1) * k + (int)a.z0) * plane_sz + rowoff[r2];
+                    const vox_t bit = (vox_t)(zl0 + (p - 1) * kz + (int)a.z0) * plane_sz + rowoff[r2];   // FINAL: zmul == 1
                     wpre[r2] = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
                 }
             }
@@ -309,7 +313,7 @@ struct Flood5 {
                 const float* fb = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW + tbase;
                 // z of the three outputs this plane feeds.  An output outside the grid (only at the ends of a march) is never
                 // written; its index may fall up to k entries outside the pz table, i.e. inside py or the float planes.
-                const int zC = zl0 + p * k + (int)a.z0;
+                const int zC = (zl0 + p * kz + (int)a.z0) * a.zmul + a.zadd;
                 const float qn = -lut[2 * MAXN + zC + k], qc = -lut[2 * MAXN + zC], qp = -lut[2 * MAXN + zC - k];
                 const float2 nq[3] = {make_float2(qn, qn), make_float2(qc, qc), make_float2(qp, qp)};
                 uint32_t g[RPT][3][2], carry[RPT][3][2];   // [row][target][voxel]
@@ -384,7 +388,7 @@ struct Flood5 {
             }
             // ---- output plane p-1 is complete ---------------------------------------------------------------------
             if (T2 && p >= 1) {
-                const vox_t zoff = (vox_t)(zl0 + (p - 1) * k) * plane_sz;
+                const vox_t zoff = (vox_t)(zl0 + (p - 1) * kz) * plane_sz;
                 // ring word offsets of the planes p-2 (N group), p-1 (C group), p (P group)
                 const uint32_t offN = (uint32_t)(((p - 1) & 3) * C::SLOT * 4), offC = (uint32_t)((p & 3) * C::SLOT * 4),
                                offP = (uint32_t)(((p + 1) & 3) * C::SLOT * 4);   // bytes
@@ -443,11 +447,12 @@ struct Flood5 {
         };
 #pragma unroll 1
         for (int ci = 0; ci < a.cols; ++ci) {
-            const int rz = rzg * a.cols + ci;
-            if (rz >= a.res_z) break;
-            zl0 = rz + sz * a.lz * k;                              // slab-local z of the first output plane
+            const int ri = rzg * a.cols + ci;
+            if (ri >= a.res_z) break;
+            const int rz = ri * a.rz_step + a.rz_off;
+            zl0 = rz + sz * a.lz * kz;                             // slab-local z of the first output plane
             if (zl0 >= (int)a.T) break;                            // (later columns start even higher)
-            steps = min(a.lz, ((int)a.T - zl0 + k - 1) / k);
+            steps = min(a.lz, ((int)a.T - zl0 + kz - 1) / kz);
             if (ci > 0) __syncthreads();                           // the previous column's planes have been consumed
 #pragma unroll
             for (int r = 0; r < RPT; ++r) aN[r][0] = aN[r][1] = bN[r][0] = bN[r][1] = bC[r][0] = bC[r][1] = NONE;
@@ -513,9 +518,18 @@ EncodeTiledFn encode_tiled() {
 // 1 = not taken (the caller runs jfa_pass_flood4), VPB_OK = launched, negative = error.
 // `mid` is the state of slab-local plane 0; planes [-below_planes, T + above_planes) around it are addressable
 // (contiguous buffer) and inside the grid.
+// res_step / res_off: only the output planes zl of the slab with zl mod res_step == res_off are produced (res_step divides k,
+// so these are whole z-lattice columns).  A pass with an even step couples only planes of equal parity; the z-slab driver
+// runs the even and the odd planes as two launches and moves the halo planes of one behind the other (multi.py).
 int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k,
-                           const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st) {
+                           const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t res_step,
+                           uint32_t res_off, uint32_t zmul, uint32_t zadd) {
+    // zmul > 1: the buffers hold the planes z = zl * zmul + zadd of the grid (zl = 0 .. N / zmul - 1): the z-CYCLIC layout of
+    // the multi-GPU driver, in which a pass whose step is a multiple of zmul needs no other rank's planes -- z +- k is the
+    // buffer plane zl +- k / zmul.  x and y are stepped by k, the buffer by kz = k / zmul planes; [z0, z1) are buffer planes.
     const uint32_t n = f.n, T = z1 - z0;
+    if (zmul == 0 || k % zmul != 0 || zadd >= zmul || n % zmul != 0 || (zmul > 1 && (z1 * zmul > n || sdf))) return 1;
+    const uint32_t kz = k / zmul, zn = n / zmul;
     const char* env = getenv("VPB_JFA_KERNEL");
     if (env && strcmp(env, "flood5") != 0) return 1;
     const bool pow2 = (k & (k - 1)) == 0;
@@ -528,7 +542,7 @@ int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, u
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return 1;
     // source planes around the slab that lie inside the grid (the march never reads others; the copy engine zero-fills them)
-    const uint32_t below = z0 < k ? z0 : k, above = n - z1 < k ? n - z1 : k;
+    const uint32_t below = z0 < kz ? z0 : kz, above = zn - z1 < kz ? zn - z1 : kz;
     const size_t plane = (size_t)n * n;
     CUtensorMap tmap;
     {
@@ -558,14 +572,19 @@ int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, u
         a.key_base = (uint32_t)((int64_t)((int)KEY_E0 - 2 * sh) * (int64_t)(1 << 23));
     }
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
+    a.kz = (int)kz; a.zmul = (int)zmul; a.zadd = (int)zadd; a.zn = (int)zn;
     a.zbias = (int)below;
     a.neg_zero = -0.0f;
     a.glut = jfa_lut_launch(f, st);
     if (!a.glut) return VPB_ERR_CUDA;
-    const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
+    const int cz = (int)((T + kz - 1) / kz);                    // lattice points per z column inside the slab
     a.lz = cz < VPB_F5_LZ ? cz : VPB_F5_LZ;
     a.segs_z = (cz + a.lz - 1) / a.lz;
-    const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
+    const uint32_t res_y = k < n ? k : n;
+    uint32_t res_z = kz < T ? kz : T;
+    if (res_step == 0 || res_off >= res_step || kz % res_step != 0 || res_z % res_step != 0) return 1;
+    res_z /= res_step;
+    a.rz_step = (int)res_step; a.rz_off = (int)res_off;
     a.tiles_y = (cy + 15) / 16;
     a.res_z = (int)res_z;
     a.cols = a.lz < 8 ? (8 / a.lz < (int)res_z ? 8 / a.lz : (int)res_z) : 1;

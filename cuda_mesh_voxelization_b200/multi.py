@@ -180,14 +180,18 @@ class SlabPipeline:
         self.overlap_halo = False
         if not self.peer:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
-            want_dma = (comm is None and world > 1 and os.environ.get("VPB_HALO", "push") != "nccl"
+            want_dma = (comm is None and world > 1 and os.environ.get("VPB_HALO", "split") != "nccl"
                         and all(k < p.T for k in self.steps))
             if want_dma:
                 try:
                     self._setup_dma()
-                    self.dma = "push" if os.environ.get("VPB_HALO", "push") in ("push", "dma") else "pull"
+                    mode = os.environ.get("VPB_HALO", "split")
+                    self.dma = {"push": "push", "dma": "push", "pull": "pull"}.get(mode, "split")
+                    if self.dma == "split" and (p.T % 2 or len(self.steps) < 2 or self.esz != 4 or n % 64 or
+                                                os.environ.get("VPB_JFA_KERNEL", "flood5") != "flood5"):
+                        self.dma = "push"      # the parity-split pass exists in the 32-bit TMA flood kernel only
                 except Exception as e:  # no symmetric-memory support on this box: NCCL halo exchange instead
-                    if os.environ.get("VPB_HALO") in ("dma", "push", "pull"):
+                    if os.environ.get("VPB_HALO") in ("dma", "push", "pull", "split"):
                         raise
                     import sys
                     print(f"[vpb200] symmetric-memory halo pull unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
@@ -207,6 +211,19 @@ class SlabPipeline:
         else:
             self.sdf = torch.empty(self.slab_voxels, dtype=torch.float32, device=self.device)
         self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
+        # z-cyclic first phase (early kernel + the passes k >= world without any exchange, then one transpose into the
+        # slabs): pays from 4 GPUs on, where thin slabs shorten the z-lattice columns of the large steps and the first halo
+        # exchange is the largest (profiles/r02_multi_gpu_notes.md).  VPB_CYCLIC=1 / 0 forces it on (from 2 ranks) / off.
+        want = os.environ.get("VPB_CYCLIC", "auto")
+        local_cyclic = comm is not None and getattr(comm, "cyclic", False)
+        w = world
+        self.cyclic = bool((self.dma == "split" or local_cyclic) and not self.peer and want != "0" and (w >= 4 or want == "1" or local_cyclic)
+                           and w >= 2 and (w & (w - 1)) == 0 and self.use_early and self.esz == 4 and n % 64 == 0
+                           and (n // 8) % w == 0 and any(k < w for k in self.steps) and any(k >= w for k in self.steps) and p.T % w == 0
+                           and os.environ.get("VPB_JFA_KERNEL", "flood5") == "flood5")
+        if self.cyclic:
+            self.cyc = [torch.empty(self.slab_voxels, **i32) for _ in range(2)]
+            self.tstreams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(4)]
         self.scratch = None
         self.pass_events = []
         self.early_events = []
@@ -242,8 +259,14 @@ class SlabPipeline:
         # the fused early kernel in work-sharing form (each rank 1/world of the lattices, results stored straight into the
         # owners' slabs over NVLink) needs the slabs mapped everywhere, i.e. this mode; VPB_EARLY_DIST=0 turns it off
         self.dist_early = (self.use_early and (self.n // 8) % p.world == 0 and os.environ.get("VPB_EARLY_DIST", "1") != "0")
-        self.side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        # the side streams carry the halo copies and the flag kernels behind them; high priority so that a flag kernel gets an SM
+        # slot while a pass is running (VPB_SIDE_PRIORITY=0: default priority, for A/B runs)
+        prio = -1 if os.environ.get("VPB_SIDE_PRIORITY", "1") != "0" else 0
+        self.side = [torch.cuda.Stream(device=self.device, priority=prio) for _ in range(2)]
         self.side_done = [torch.cuda.Event() for _ in range(2)]
+        # split mode: pushes in flight that still read the centre of state buffer i (flood_split)
+        self.push_events = [[], []]
+        self.trace = [] if os.environ.get("VPB_SPLIT_TRACE") == "1" else None    # (k, parity, wait start, wait end, launch end)
         # the exchange of pass i+1 behind the interior of pass i (flood_overlapped).  Opt-in (VPB_HALO_OVERLAP=1): measured on
         # 2 x B200 at 1024^3 it hides half of the exchange (0.89 -> 0.47 ms per step) but the two boundary launches march one
         # plane per z-lattice column (three staged planes per output instead of ~1.1) and cost 1.7 ms more than they save:
@@ -356,7 +379,7 @@ class SlabPipeline:
                         self.side_done[i].record(st)
                     main.wait_event(self.side_done[i])
 
-            if self.dma == "push":
+            if self.dma in ("push", "split"):
                 # write my boundary planes into the neighbours' halo regions, then the barrier: after it every rank's
                 # halos are complete.  A neighbour's halo of this buffer was last read two passes ago, before the
                 # barrier that preceded my previous pass.
@@ -448,6 +471,146 @@ class SlabPipeline:
         self.symm[dstbuf].barrier(channel=0)
         self._mark(record, "exchange")
 
+    # signal channels of the split mode (channel 0 carries the barriers, 1 the peer mode's): "my low / high boundary planes of
+    # parity q are in your halo" = CH_LOW + q / CH_HIGH + q
+    CH_LOW, CH_HIGH = 2, 4
+    SIGNAL_TIMEOUT_MS = 20000      # a lost signal must fail the step, not hang the GPU
+
+    def _wait_parity(self, q):
+        """The compute stream waits until both neighbours' boundary planes of parity q are in this rank's halos."""
+        p, sig = self.plan, self.symm[0]
+        if p.rank > 0:
+            sig.wait_signal(p.rank - 1, self.CH_HIGH + q, self.SIGNAL_TIMEOUT_MS)
+        if p.rank + 1 < p.world:
+            sig.wait_signal(p.rank + 1, self.CH_LOW + q, self.SIGNAL_TIMEOUT_MS)
+
+    def flood_split(self, k, nxt, cur, wait_halos, record=False):
+        """One pass with an EVEN step as two launches -- the even and the odd planes of the slab, which such a pass does not
+        couple (z +- k has the parity of z) -- with the halo exchange of the NEXT pass (step nxt) behind them and NO barrier.
+        When the launch of parity q is done, copy engines write its boundary planes (the planes of parity q among the lowest
+        and the highest nxt of the slab; one strided copy per neighbour, vpb_copy_planes_dev) into the neighbours' halo
+        regions of the destination buffer on two side streams and raise a flag in each neighbour's symmetric-memory signal
+        pad; the next pass's launch of parity q waits for the neighbours' flags (device-side, on the compute stream).  The
+        copies of the even planes travel while the odd planes are computed and the other way round.
+        Hazards: a neighbour's halo planes of parity q in the destination buffer were last read by its parity-q launch of
+        the previous pass, which finished before it raised the flag this rank's parity-q launch waited for; the centre
+        planes a copy reads are overwritten two passes later, after the compute stream has waited for it (push_events)."""
+        torch, p, n = self.torch, self.plan, self.n
+        main = torch.cuda.current_stream()
+        dstbuf = 1 - cur
+        for ev in self.push_events[dstbuf]:
+            main.wait_event(ev)
+        self.push_events[dstbuf] = []
+        sig = self.symm[0]
+        pb = self.plane * 4                                   # bytes per plane
+        mid = self.center(cur).data_ptr()
+        dst = self.center(dstbuf).data_ptr()
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for q in (0, 1):
+            if record and self.trace is not None:
+                t0 = torch.cuda.Event(enable_timing=True); t0.record()
+            if wait_halos:
+                self._wait_parity(q)
+            if record and self.trace is not None:
+                t1 = torch.cuda.Event(enable_timing=True); t1.record()
+            rc = self.lib.vpb_jfa_pass_part_dev(ctypes.c_void_p(mid), ctypes.c_void_p(dst), n, p.z0, p.z1, k, self.vs, self._o(),
+                                                2, q, self._stream())
+            if rc != 0:
+                self.capi.check(rc if rc < 0 else -1)
+            done = torch.cuda.Event(enable_timing=bool(record and self.trace is not None))
+            done.record(main)
+            if record and self.trace is not None:
+                self.trace.append((k, q, t0, t1, done))
+            # planes of parity q among [0, nxt) -> lower neighbour's upper halo, among [T - nxt, T) -> upper neighbour's lower halo
+            cnt = (nxt - q + 1) // 2 if nxt > q else 0       # p.T and T - nxt... are even for nxt >= 2; nxt == 1: plane 0 / T-1
+            jobs = []
+            if p.rank > 0:
+                first = q                                    # first plane of parity q in [0, nxt)
+                jobs.append((p.rank - 1, first, (p.H + p.T + first), cnt, self.CH_LOW + q))
+            if p.rank + 1 < p.world:
+                first = p.T - nxt + ((p.T - nxt + q) % 2)    # first plane of parity q in [T - nxt, T)
+                c_hi = len(range(first, p.T, 2))
+                jobs.append((p.rank + 1, first, (p.H - p.T + first), c_hi, self.CH_HIGH + q))
+            for side, (nb, first, at, c, ch) in enumerate(jobs):
+                st = self.side[side]
+                st.wait_event(done)
+                with torch.cuda.stream(st):
+                    if c > 0:
+                        self.capi.check(self.lib.vpb_copy_planes_dev(
+                            ctypes.c_void_p(self.peer_ext[dstbuf][nb].data_ptr() + at * pb), 2 * pb,
+                            ctypes.c_void_p(dst + first * pb), 2 * pb, pb, c, ctypes.c_void_p(st.cuda_stream)))
+                    sig.put_signal(nb, ch, self.SIGNAL_TIMEOUT_MS)
+                    pushed = torch.cuda.Event()
+                    pushed.record(st)
+                self.push_events[dstbuf].append(pushed)
+        if record:
+            e1.record()
+            self.pass_events.append((k, e0, e1))
+
+    def cyclic_phase(self, targets, buf, record=False):
+        """Seed extraction + every pass with k >= world in the z-cyclic layout (this rank's planes z = rank mod world as a
+        dense buffer): no exchange, full-length z-lattice columns; then the transpose into z-slabs, hidden behind the last of
+        these passes.  My planes inside rank d's slab are T / world consecutive planes of the cyclic buffer and every
+        world-th plane of d's slab, starting at plane `rank`: the last pass runs as `world` launches, one destination each
+        (my own last), and when a launch is done ONE strided copy-engine copy (vpb_copy_planes_dev) moves its planes into
+        the centre of d's extended buffer `buf` (targets[d]: that buffer, mapped into this process) while the next launch
+        runs.  The caller synchronises the ranks afterwards."""
+        p, n, W = self.plan, self.n, self.plan.world
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = self.lib.vpb_jfa_early_cyclic_dev(_ptr(self.grid_full), n, self.vs, self._o(), W, p.rank, _ptr(self.cyc[0]),
+                                               _ptr(self.cyc[1]), self._stream())
+        if rc != 0:
+            self.capi.check(rc if rc < 0 else -1)
+        if record:
+            e1.record()
+            self.early_events.append((e0, e1))
+        self._mark(record, "seed")
+        c = 1
+        ks = [k for k in self.steps if k >= W]
+        pb = self.plane * 4
+        tc = p.T // W
+        used = []
+        for k in ks:
+            last = k == ks[-1]
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            parts = [((p.rank + 1 + i) % W) for i in range(W)] if last else [None]
+            for i, d in enumerate(parts):
+                lo, hi = (0, p.T) if d is None else (d * tc, (d + 1) * tc)
+                rc = self.lib.vpb_jfa_pass_cyclic_dev(_ptr(self.cyc[c]), _ptr(self.cyc[1 - c]), n, W, p.rank, k, lo, hi, self.vs,
+                                                      self._o(), self._stream())
+                if rc != 0:
+                    self.capi.check(rc if rc < 0 else -1)
+                if d is None:
+                    continue
+                done = torch.cuda.Event()
+                done.record(main)
+                st = self.tstreams[i % len(self.tstreams)]
+                st.wait_event(done)
+                used.append(st)
+                self.capi.check(self.lib.vpb_copy_planes_dev(
+                    ctypes.c_void_p(targets[d].data_ptr() + (p.H + p.rank) * pb), W * pb,
+                    ctypes.c_void_p(self.cyc[1 - c].data_ptr() + d * tc * pb), pb, pb, tc, ctypes.c_void_p(st.cuda_stream)))
+            if record:
+                e1.record()
+                self.pass_events.append((k, e0, e1))
+            c = 1 - c
+        self._mark(record, "flood")
+        for st in set(used):
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
     def flood(self, k, cur, last, record=False):
         p, n = self.plan, self.n
         if self.peer:
@@ -504,7 +667,14 @@ class SlabPipeline:
         if not sdf:
             return
         p_ = self.plan
-        if self.use_early:
+        steps = self.steps
+        if self.cyclic and self.dma == "split":
+            cur = 0
+            self.cyclic_phase(self.peer_ext[cur], cur, record_passes)
+            self.symm[cur].barrier(channel=0)          # every rank's planes have landed in every slab
+            self._mark(record_passes, "transpose")
+            steps = [k for k in self.steps if k < p_.world]
+        elif self.use_early:
             if self.peer:
                 self.peer_barrier(0)          # buffer 0 is about to become scratch: nobody may still be reading it
             if record_passes:
@@ -524,7 +694,24 @@ class SlabPipeline:
         else:
             self.seed()
             cur = 0
-        self._mark(record_passes, "seed")
+        if not (self.cyclic and self.dma == "split"):
+            self._mark(record_passes, "seed")
+        if self.dma == "split":
+            # the first pass's halos come from the early kernel's result: one ordinary push + barrier; every later exchange
+            # is hidden behind the pass before it (flood_split); the final pass (k = 1) couples both parities: one launch
+            self.exchange(steps[0], cur)
+            self._mark(record_passes, "exchange")
+            for idx, k in enumerate(steps):
+                if k > 1:
+                    self.flood_split(k, steps[idx + 1], cur, wait_halos=idx > 0, record=record_passes)
+                else:
+                    if idx > 0:
+                        self._wait_parity(0)
+                        self._wait_parity(1)
+                    self.flood(k, cur, last=True, record=record_passes)
+                self._mark(record_passes, "flood")
+                cur = 1 - cur
+            return
         overlap = self.dma == "push" and self.overlap_halo
         halos_ready = False
         for idx, k in enumerate(self.steps):
@@ -610,9 +797,10 @@ class SlabPipeline:
 class LocalComm:
     """All ranks in one process / on one GPU: exchanges become device copies.  Drives the ranks in lockstep."""
 
-    def __init__(self, dist_early=False):
+    def __init__(self, dist_early=False, cyclic=False):
         self.ranks: List[SlabPipeline] = []
         self.dist_early = dist_early
+        self.cyclic = cyclic          # emulate the z-cyclic first phase + transpose (SlabPipeline.cyclic_phase)
 
     def add(self, p: SlabPipeline):
         self.ranks.append(p)
@@ -631,15 +819,20 @@ class LocalComm:
             for q in R:
                 w = q.grid_slab.numel()
                 p.grid_full[q.plan.rank * w:(q.plan.rank + 1) * w].copy_(q.grid_slab)
-        if self.dist_early and R[0].use_early and (R[0].n // 8) % len(R) == 0:
+        steps = R[0].steps
+        if self.cyclic and all(p.cyclic for p in R):
+            for p in R:
+                p.cyclic_phase([q.ext[0] for q in R], 0)
+            steps = [k for k in steps if k < len(R)]
+        elif self.dist_early and R[0].use_early and (R[0].n // 8) % len(R) == 0:
             ptrs = [q.center(1).data_ptr() for q in R]       # all slabs on this GPU: the work-sharing early kernel, emulated
             for p in R:
                 p.early_dist(ptrs)
         else:
             for p in R:
                 p.early() if p.use_early else p.seed()
-        cur = 1 if R[0].use_early else 0
-        for k in R[0].steps:
+        cur = 0 if (self.cyclic and all(p.cyclic for p in R)) else (1 if R[0].use_early else 0)
+        for k in steps:
             for p in R:                                   # every receive pulls from the sender's current centre
                 for t in p.plan.recvs(k):
                     src = R[t.peer].center(cur)[t.src_lo * p.plane:(t.src_lo + t.count) * p.plane]

@@ -168,6 +168,33 @@ VPB_API int vpb_jfa_pass_dev(const uint32_t* src_below, const uint32_t* src_mid,
                              uint32_t* dst_slab, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k, float voxel_size,
                              const float origin[3], const uint32_t* words_full, float* sdf_slab, uint32_t* seeds_slab,
                              void* stream);
+/* A PART of one (non-final) pass: only the output planes z of the slab with (z - z0) mod res_step == res_off, res_step a
+ * divisor of k.  A pass with an even step couples only planes of equal parity, so the z-slab driver runs the even and the
+ * odd planes as two launches and hides the halo exchange of one behind the other.  src_mid = state of plane z0 in a buffer
+ * that also holds the k planes below and above the slab (where they are inside the grid).  32-bit state only; returns 1
+ * when the shape is not taken (use vpb_jfa_pass_dev). */
+VPB_API int vpb_jfa_pass_part_dev(const uint32_t* src_mid, uint32_t* dst_slab, uint32_t n, uint32_t z0, uint32_t z1, uint32_t k,
+                                  float voxel_size, const float origin[3], uint32_t res_step, uint32_t res_off, void* stream);
+/* n_planes pieces of plane_bytes, dst_stride / src_stride bytes apart, device to device (either side may be a peer GPU's
+ * memory mapped into this process) on one copy engine: the strided halo planes of vpb_jfa_pass_part_dev and the
+ * cyclic -> slab transpose of the z-cyclic passes below. */
+VPB_API int vpb_copy_planes_dev(void* dst, size_t dst_stride, const void* src, size_t src_stride, size_t plane_bytes,
+                                size_t n_planes, void* stream);
+/* z-CYCLIC multi-GPU layout: rank r of `world` owns the planes z = r (mod world), stored densely (plane z at index z / world,
+ * N / world planes).  A pass whose step is a multiple of `world` only couples planes of equal z mod world, so in this layout
+ * the early kernel and every pass with k >= world run WITHOUT any exchange and with full-length z-lattice columns; the
+ * driver then transposes once into z-slabs (vpb_copy_planes_dev) for the passes k < world.
+ * vpb_jfa_early_cyclic_dev: seed extraction + the passes k = N/2, N/4, N/8 for the rank's planes (it runs exactly the 8x8x8
+ * lattices whose z residue is = rank mod world: every store is local).  vpb_jfa_pass_cyclic_dev: one pass with step k
+ * (k % world == 0) from src to dst, both in the rank's cyclic layout, for the buffer planes [plane_lo, plane_hi) (the planes
+ * plane_lo - k/world .. plane_hi - 1 + k/world of src are read): the driver produces the last cyclic pass destination by
+ * destination and transposes one part while the next is computed.  32-bit state; both return 1 when the shape or frame
+ * is not taken (run the z-slab path). */
+VPB_API int vpb_jfa_early_cyclic_dev(const uint32_t* words_full, uint32_t n, float voxel_size, const float origin[3],
+                                     uint32_t world, uint32_t rank, uint32_t* shell_scratch, uint32_t* state_cyclic, void* stream);
+VPB_API int vpb_jfa_pass_cyclic_dev(const uint32_t* src_cyclic, uint32_t* dst_cyclic, uint32_t n, uint32_t world, uint32_t rank,
+                                    uint32_t k, uint32_t plane_lo, uint32_t plane_hi, float voxel_size, const float origin[3],
+                                    void* stream);
 /* The same pass for multi-GPU runs WITHOUT halo copies: slab_states[r] (r < world <= 8) is the device address, valid in
  * THIS process, of rank r's slab of the source state (planes [r*slab_planes, (r+1)*slab_planes), slab_planes*world == N)
  * — the ranks' buffers mapped over NVLink (CUDA IPC / torch symmetric memory).  The kernel loads the planes z-k / z+k

@@ -415,6 +415,31 @@ def test_z_slabs_are_bit_identical_to_one_gpu(world, dist_early, meshes, oracle,
     assert np.array_equal(sdf.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
 
 
+@pytest.mark.parametrize("n", [128, 256])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_z_cyclic_first_phase_is_bit_identical_to_one_gpu(world, n, meshes, oracle, vpb):
+    """The z-cyclic multi-GPU path emulated on one GPU: every rank keeps the planes z = rank (mod world), runs seed extraction
+    + the passes k >= world there without any exchange (vpb_jfa_early_cyclic_dev, vpb_jfa_pass_cyclic_dev), then the planes
+    are transposed into z-slabs (vpb_copy_planes_dev) for the passes k < world.  Result == the oracle's, bit for bit."""
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    from cuda_mesh_voxelization_b200.multi import LocalComm, SlabPipeline
+    names = ["bimba", "bunny"]
+    origin, vs = _frame(oracle, meshes, names, n)
+    dm = [DeviceMesh(*meshes[m], "cuda:0") for m in names]
+    comm = LocalComm(cyclic=True)
+    for r in range(world):
+        comm.add(SlabPipeline(n, vs, origin, r, world, comm=comm))
+    assert all(p.cyclic for p in comm.ranks)
+    sdf = comm.run_all(dm, op=capi.OP_UNION)
+    torch.cuda.synchronize()
+    words = np.concatenate([p.grid_slab.cpu().numpy().view(np.uint32) for p in comm.ranks])
+    want = oracle.csg(oracle.voxelize(*meshes["bimba"], n, vs, origin), oracle.voxelize(*meshes["bunny"], n, vs, origin), n, 1)
+    assert np.array_equal(words, want)
+    assert np.array_equal(sdf.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
+
+
 def test_full_size_1024_properties(meshes, oracle, vpb):
     """BASELINE's metric configuration (1024^3, 1 348 128 faces ∪ bimba): occupancy bit-exact against the oracle;
     the SDF (too large for the CPU oracle) through size-independent properties."""
