@@ -339,15 +339,20 @@ def run_ours(args):
         print(f"[trace rank {rank}] {line}", file=sys.stderr, flush=True)
     partition_label = None
     if world > 1 and not replicas:
-        halo = {"split": "every pass runs as two half-slab launches; when a half is done copy engines write its boundary planes "
-                         "into the neighbour's symmetric-memory halo over NVLink and raise a flag there, the half that needs them "
-                         "waits for the flag on the device: the exchange of pass i+1 hides behind pass i, no barriers",
+        halo = {"split": "slab passes run as two launches, the even and the odd planes (an even step does not couple them); when a "
+                         "launch is done copy engines write its boundary planes into the neighbours' symmetric-memory halos over "
+                         "NVLink and raise a flag there, the next pass's launch of that parity waits for the flags on the device: "
+                         "the exchange of pass i+1 hides behind pass i, no barriers",
                 "push": "halo planes written into the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
                         "device-side barrier per pass",
                 "pull": "halo planes read from the neighbours' symmetric-memory buffers by copy engines over NVLink, one "
                         "device-side barrier per pass"}.get(pipe.dma, "NCCL send/recv halo exchange per pass")
         early = ("fused early passes work-shared (each rank 1/N of the lattices, stored into the owners' slabs over NVLink)"
                  if pipe.dma and getattr(pipe, "dist_early", False) else "fused early passes run per rank, exchange-free")
+        if getattr(pipe, "cyclic", False):
+            early = (f"z-cyclic first phase: rank r keeps the planes z = r (mod {world}); seed extraction, the fused early passes and "
+                     f"every pass with k >= {world} run there with NO exchange (each rank 1/{world} of the lattices, all stores local), "
+                     "then one transpose into z-slabs by strided copy-engine copies hidden behind the last of these passes")
         partition_label = f"{halo}; {early}"
     # dominant kernel: the JFA flood pass (all but the cheap first passes run ~the same code at full density)
     pass_ms = {}
