@@ -459,10 +459,13 @@ int vpb_jfa_pass_cyclic_dev(const uint32_t* src, uint32_t* dst, uint32_t n, uint
     VPB_REQUIRE(n > 0 && n <= kMaxJfaN && world >= 1 && rank < world && n % world == 0 && k >= 1 && k < n,
                 "jfa_pass_cyclic: bad n=%u rank %u of %u k=%u", n, rank, world, k);
     VPB_REQUIRE(plane_lo < plane_hi && plane_hi <= n / world, "jfa_pass_cyclic: bad plane range [%u,%u) of %u", plane_lo, plane_hi, n / world);
-    if (jfa_state64(n) || k % world != 0) return 1;
+    if (k % world != 0) return 1;
+    const Frame f = make_frame(n, vs, origin);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
+    if (jfa_state64(n)) return jfa_pass_flood4_cyclic_launch_s64(src, dst, f, plane_lo, plane_hi, k, world, rank, st);
     const size_t off = (size_t)plane_lo * n * n;
-    return jfa_pass_flood5_launch(src + off, dst + off, make_frame(n, vs, origin), plane_lo, plane_hi, k, nullptr, nullptr, nullptr,
-                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, 1, 0, world, rank);
+    const int rc = jfa_pass_flood5_launch(src + off, dst + off, f, plane_lo, plane_hi, k, nullptr, nullptr, nullptr, st, 1, 0, world, rank);
+    return rc == 1 ? jfa_pass_flood4_cyclic_launch(src, dst, f, plane_lo, plane_hi, k, world, rank, st) : rc;
 }
 
 int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes, uint32_t* dst,

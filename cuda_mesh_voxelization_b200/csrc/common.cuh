@@ -159,6 +159,10 @@ int jfa_early_launch(const uint32_t* words_full, const Frame& f, uint32_t z0, ui
 // the same with the seed-shell bits already in `shell` (csg_shell_launch wrote them): no shell kernel
 int jfa_early_from_shell_launch(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
 int jfa_early_from_shell_launch_s64(const uint32_t* shell, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* state, cudaStream_t st);
+int jfa_pass_flood4_cyclic_launch(const uint32_t* src, uint32_t* dst, const Frame& f, uint32_t plane_lo, uint32_t plane_hi,
+                                  uint32_t k, uint32_t zmul, uint32_t zadd, cudaStream_t st);
+int jfa_pass_flood4_cyclic_launch_s64(const uint32_t* src, uint32_t* dst, const Frame& f, uint32_t plane_lo, uint32_t plane_hi,
+                                      uint32_t k, uint32_t zmul, uint32_t zadd, cudaStream_t st);
 // z-cyclic multi-GPU form: rank's planes z = rank (mod world) as a dense buffer (jfa_early.cu)
 int jfa_early_cyclic_launch(const uint32_t* words_full, const Frame& f, uint32_t world, uint32_t rank, uint32_t* shell_scratch,
                             uint32_t* state, cudaStream_t st);

@@ -65,8 +65,11 @@ struct F4Args {
     uint32_t* seeds;          // FINAL only, optional
     const float* glut;        // px | py | pz, 3 * MAXN floats
     uint32_t n, z0, T;
-    int k;
-    int contiguous;           // src[2] == src[1] + k planes and src[0] == src[1] - k planes
+    int k;                    // step of the pass in voxels (x, y; and z unless the planes are z-cyclic)
+    int kz;                   // the same step in PLANES of the buffers (k, or k / zmul: see jfa_pass_flood5_launch)
+    int zmul, zadd;           // grid z of buffer plane zl (slab-local) = (zl + z0) * zmul + zadd   (1, 0 for a z-slab)
+    int zn;                   // (zl + z0) in [0, zn) <=> the plane is inside the grid
+    int contiguous;           // src[2] == src[1] + kz planes and src[0] == src[1] - kz planes
     int lz, segs_z;           // outputs per march segment, segments per z-lattice column
     int res_z, cols;          // z residues (= z-lattice columns) in the slab; consecutive columns walked by one CTA
     int tiles_y;              // TR-row tiles per y-lattice column
@@ -149,7 +152,7 @@ struct Flood4 {
 
     static __device__ __forceinline__ void run(const F4Args& a) {
         extern __shared__ __align__(16) float sm[];
-        const int n = (int)a.n, k = a.k;
+        const int n = (int)a.n, k = a.k, kz = a.kz;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         // ring-entry offset of the candidate with in-plane code r*4 + c (row r, column c): r * W + c * SS
         __shared__ uint32_t s_dec[16];
@@ -196,9 +199,9 @@ struct Flood4 {
         const int tbase = 2 * warp * C::W + 2 * lane;              // candidate (rho, c) of this thread: tbase + rho*W + c*SS
 
         state_t stq[C::NP][C::G];
-        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * k + (int)a.z0; return gz >= 0 && gz < n; };
+        auto plane_in_grid = [&](int p) { const int gz = zl0 + p * kz + (int)a.z0; return gz >= 0 && gz < a.zn; };
         auto fetch = [&](int p) {
-            const int zl = zl0 + p * k;
+            const int zl = zl0 + p * kz;
             const state_t* pp = a.contiguous ? a.src[1] + (ptrdiff_t)zl * (ptrdiff_t)plane_sz
                                               : (p < 0 ? a.src[0] : (p == 0 ? a.src[1] : a.src[2])) + (size_t)zl0 * plane_sz;
 #pragma unroll
@@ -279,16 +282,17 @@ struct Flood4 {
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
                     if (!ok[r2]) continue;
-                    const vox_t bit = ((vox_t)(zl0 + (p - 1) * k + (int)a.z0) * n + (gy0 + r2 * k)) * n + x0;
+                    const vox_t bit = ((vox_t)(zl0 + (p - 1) * kz + (int)a.z0) * n + (gy0 + r2 * k)) * n + x0;   // FINAL: zmul == 1
                     wpre[r2] = __ldg(a.words + (bit >> 5)) >> (bit & 31u);
                 }
             }
             if (ok[0] && in_grid) {
                 const float* fb = fbuf + (C::NBUF == 2 ? (p & 1) : 0) * 3 * C::PW + tbase;
                 const uint32_t tag = (uint32_t)(((p + 1) & 3) * C::PW);
-                const int zN = min(max(zl0 + (p + 1) * k + (int)a.z0, 0), MAXN - 1);
-                const int zC = min(max(zl0 + p * k + (int)a.z0, 0), MAXN - 1);
-                const int zP = min(max(zl0 + (p - 1) * k + (int)a.z0, 0), MAXN - 1);
+                const int zg = (zl0 + p * kz + (int)a.z0) * a.zmul + a.zadd;     // grid z of plane p; its neighbours are k away
+                const int zN = min(max(zg + k, 0), MAXN - 1);
+                const int zC = min(max(zg, 0), MAXN - 1);
+                const int zP = min(max(zg - k, 0), MAXN - 1);
                 const float qn = -lut[2 * MAXN + zN], qc = -lut[2 * MAXN + zC], qp = -lut[2 * MAXN + zP];
                 const float2 nq[3] = {make_float2(qn, qn), make_float2(qc, qc), make_float2(qp, qp)};
                 uint32_t g[2][3][2], carry[2][3][2], ownk[2][2];   // [row][target][voxel]
@@ -385,7 +389,7 @@ struct Flood4 {
             }
             // ---- output plane p-1 is complete ---------------------------------------------------------------------
             if (T2 && p >= 1) {
-                const int zl = zl0 + (p - 1) * k;
+                const int zl = zl0 + (p - 1) * kz;
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
                     if (!ok[r2]) continue;
@@ -432,9 +436,9 @@ struct Flood4 {
         for (int ci = 0; ci < a.cols; ++ci) {
             const int rz = rzg * a.cols + ci;
             if (rz >= a.res_z) break;
-            zl0 = rz + sz * a.lz * k;                              // slab-local z of the first output plane
+            zl0 = rz + sz * a.lz * kz;                             // slab-local z of the first output plane
             if (zl0 >= (int)a.T) break;                            // (later columns start even higher)
-            steps = min(a.lz, ((int)a.T - zl0 + k - 1) / k);
+            steps = min(a.lz, ((int)a.T - zl0 + kz - 1) / kz);
             if (ci > 0) __syncthreads();                           // the previous column's last plane has been consumed
 #pragma unroll
             for (int s = 0; s < 3; ++s)
@@ -494,10 +498,13 @@ int launch_ss(const F4Args& a, dim3 grid, bool fin, cudaStream_t st) {
 
 // Dispatcher of the key-based flood passes: v4 for N % 64 == 0, k a power of two with at least 8 lattice rows in y;
 // otherwise (and with VPB_JFA_KERNEL=flood3) v3, which itself falls back to the z-march / gather kernels.
-int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
-                                   const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
-                                   float* sdf, uint32_t* seeds, cudaStream_t st) {
+static int flood4_launch_impl(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                              const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                              float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t zmul, uint32_t zadd) {
     const uint32_t n = f.n, T = z1 - z0;
+    const bool cyclic = zmul > 1;              // buffer planes are the grid planes z = zl * zmul + zadd (see jfa_pass_flood5_launch)
+    if (zmul == 0 || k % zmul != 0 || zadd >= zmul || n % zmul != 0 || (cyclic && (z1 * zmul > n || sdf))) return 1;
+    const uint32_t kz = k / zmul, zn = n / zmul;
     const char* env = getenv("VPB_JFA_KERNEL");
     const bool force3 = env && strcmp(env, "flood3") == 0;
     const bool pow2 = (k & (k - 1)) == 0;
@@ -507,7 +514,7 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
 #ifndef VPB_STATE64
     {   // v5 (TMA-staged planes) takes the common case: source planes contiguous around the slab, >= 16 lattice rows
         const ptrdiff_t kp5 = (ptrdiff_t)k * n * n;
-        if (!force3 && above == mid + kp5 && below == mid - kp5) {
+        if (!force3 && !cyclic && above == mid + kp5 && below == mid - kp5) {
             const int rc = jfa_pass_flood5_launch(mid, dst, f, z0, z1, k, words_full, sdf, seeds, st, 1, 0, 1, 0);
             if (rc <= 0) return rc;
         }
@@ -515,21 +522,22 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
 #endif
     F4Args a;
     if (force3 || n % SEG != 0 || n > MAXN || !pow2 || !align_ok || cy < 8 || !jfa_frame_supports_keys(f, &a.key_base, &a.bigz))
-        return VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+        return cyclic ? 1 : VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
     a.src[0] = below; a.src[1] = mid; a.src[2] = above;
     a.dst = dst; a.words = words_full; a.sdf = sdf; a.seeds = seeds;
     a.key_k0 = 0u - a.key_base * 16u;
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
+    a.kz = (int)kz; a.zmul = (int)zmul; a.zadd = (int)zadd; a.zn = (int)zn;
     a.neg_zero = -0.0f;
     a.ox = f.ox; a.oy = f.oy; a.oz = f.oz; a.vs4 = f.vs * 0.25f;
     a.glut = VPB_SFX(jfa_lut_launch)(f, st);
     if (!a.glut) return VPB_ERR_CUDA;
-    const ptrdiff_t kp = (ptrdiff_t)k * n * n;
+    const ptrdiff_t kp = (ptrdiff_t)kz * n * n;
     a.contiguous = (above == mid + kp) && (below == mid - kp);
-    const int cz = (int)((T + k - 1) / k);                      // lattice points per z column inside the slab
+    const int cz = (int)((T + kz - 1) / kz);                    // lattice points per z column inside the slab
     a.lz = a.contiguous ? (cz < VPB_F4_LZ ? cz : VPB_F4_LZ) : 1;
     a.segs_z = (cz + a.lz - 1) / a.lz;
-    const uint32_t res_y = k < n ? k : n, res_z = k < T ? k : T;
+    const uint32_t res_y = k < n ? k : n, res_z = kz < T ? kz : T;
     const int tr = cy >= 16 ? 16 : 8;
     a.tiles_y = (cy + tr - 1) / tr;
     // short marches (thin slabs, large k): one CTA walks several z-lattice columns, so the tables, the staging offsets and
@@ -547,7 +555,7 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
             case 8: return launch_ss<8, 8>(a, grid, fin, st);
             default: break;   // k <= 4 with fewer than 16 lattice rows would need N < 64
         }
-        return VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
+        return cyclic ? 1 : VPB_F4_FALLBACK(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st);
     }
     switch (k >= 64 ? 64 : (int)k) {
         case 64: return launch_ss<64, 16>(a, grid, fin, st);
@@ -558,6 +566,24 @@ int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, con
         case 2: return launch_ss<2, 16>(a, grid, fin, st);
         default: return launch_ss<1, 16>(a, grid, fin, st);
     }
+}
+
+int VPB_SFX(jfa_pass_flood_launch)(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
+                                   const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
+                                   float* sdf, uint32_t* seeds, cudaStream_t st) {
+    return flood4_launch_impl(below, mid, above, dst, f, z0, z1, k, words_full, sdf, seeds, st, 1, 0);
+}
+
+// z-cyclic layout (see jfa_pass_flood5_launch): src / dst are the rank's dense buffers of the planes z = zadd (mod zmul), the
+// launch produces the buffer planes [plane_lo, plane_hi).  1 = shape not taken.
+int VPB_SFX(jfa_pass_flood4_cyclic_launch)(const uint32_t* src_, uint32_t* dst_, const Frame& f, uint32_t plane_lo, uint32_t plane_hi,
+                                           uint32_t k, uint32_t zmul, uint32_t zadd, cudaStream_t st) {
+    if (zmul == 0 || k % zmul != 0) return 1;
+    const size_t plane = (size_t)f.n * f.n;
+    const state_t* mid = reinterpret_cast<const state_t*>(src_) + plane_lo * plane;
+    const ptrdiff_t kp = (ptrdiff_t)(k / zmul) * (ptrdiff_t)plane;
+    return flood4_launch_impl(mid - kp, mid, mid + kp, reinterpret_cast<state_t*>(dst_) + plane_lo * plane, f, plane_lo, plane_hi, k,
+                              nullptr, nullptr, nullptr, st, zmul, zadd);
 }
 
 }  // namespace vpb

@@ -154,6 +154,21 @@ class SlabPipeline:
         self.w32 = self.esz // 4
         self.plane = n * n * self.w32
         self.bit_plane = n * n
+        # z-cyclic first phase (early kernel + the passes k >= world without any exchange, then one transpose into the
+        # slabs): pays from 4 GPUs on, where thin slabs shorten the z-lattice columns of the large steps and the first halo
+        # exchange is the largest (profiles/r02_multi_gpu_notes.md).  VPB_CYCLIC=1 / 0 forces it on (from 2 ranks) / off.
+        import os
+        want_cyc = os.environ.get("VPB_CYCLIC", "auto")
+        local_cyclic = comm is not None and getattr(comm, "cyclic", False)
+        w = world
+        cyc_elig = bool(want_cyc != "0" and (w >= 4 or want_cyc == "1" or local_cyclic) and w >= 2 and (w & (w - 1)) == 0
+                        and self.use_early and n % 64 == 0 and (n // 8) % w == 0 and p.T % w == 0
+                        and any(k < w for k in self.steps) and any(k >= w for k in self.steps)
+                        and (comm is None or local_cyclic)
+                        and os.environ.get("VPB_JFA_KERNEL", "flood5") == "flood5")
+        h_full = p.H
+        if cyc_elig:
+            p.H = max(k for k in self.steps if k < w)     # the slab phase only runs the steps below `world`
         i32 = dict(dtype=torch.int32, device=self.device)
         self.grid_full = torch.zeros(capi.n_words(n), **i32)
         wslab = self.bit_plane * p.T // 32
@@ -161,7 +176,6 @@ class SlabPipeline:
         self.grid_b = torch.empty(wslab, **i32)
         # peer mode: state in symmetric memory, read by the neighbours' kernels over NVLink (needs N % 64 == 0 for the
         # key-based flood kernel); opt-in, see the module docstring for the measurement
-        import os
         if peer is None:
             peer = os.environ.get("VPB_PEER") == "1" and comm is None and world > 1 and n % 64 == 0 and self.esz == 4
         self.peer = bool(peer)
@@ -177,6 +191,7 @@ class SlabPipeline:
                 print(f"[vpb200] peer mode unavailable ({type(e).__name__}: {e}); using the NCCL halo exchange", file=sys.stderr)
                 self.peer = False
         self.dma = False
+        self.cyclic = False
         self.overlap_halo = False
         if not self.peer:
             # extended state buffers [H | T | H] planes, two of them (ping-pong), + two far-slab receive buffers
@@ -197,6 +212,9 @@ class SlabPipeline:
                     print(f"[vpb200] symmetric-memory halo pull unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
                           file=sys.stderr)
                     self.symm = None
+            self.cyclic = cyc_elig and (self.dma in ("split", "push") or local_cyclic)
+            if cyc_elig and not self.cyclic:                # no symmetric memory after all: the ordinary slab path
+                p.H = h_full
             if not self.dma:
                 self.ext = [torch.zeros((p.H + p.T + p.H) * self.plane, **i32) for _ in range(2)]
             # far-slab receive buffers (k >= T passes), only the sides this rank ever receives on
@@ -211,18 +229,8 @@ class SlabPipeline:
         else:
             self.sdf = torch.empty(self.slab_voxels, dtype=torch.float32, device=self.device)
         self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
-        # z-cyclic first phase (early kernel + the passes k >= world without any exchange, then one transpose into the
-        # slabs): pays from 4 GPUs on, where thin slabs shorten the z-lattice columns of the large steps and the first halo
-        # exchange is the largest (profiles/r02_multi_gpu_notes.md).  VPB_CYCLIC=1 / 0 forces it on (from 2 ranks) / off.
-        want = os.environ.get("VPB_CYCLIC", "auto")
-        local_cyclic = comm is not None and getattr(comm, "cyclic", False)
-        w = world
-        self.cyclic = bool((self.dma == "split" or local_cyclic) and not self.peer and want != "0" and (w >= 4 or want == "1" or local_cyclic)
-                           and w >= 2 and (w & (w - 1)) == 0 and self.use_early and self.esz == 4 and n % 64 == 0
-                           and (n // 8) % w == 0 and any(k < w for k in self.steps) and any(k >= w for k in self.steps) and p.T % w == 0
-                           and os.environ.get("VPB_JFA_KERNEL", "flood5") == "flood5")
         if self.cyclic:
-            self.cyc = [torch.empty(self.slab_voxels, **i32) for _ in range(2)]
+            self.cyc = [torch.empty(self.slab_voxels * self.w32, **i32) for _ in range(2)]
             self.tstreams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(4)]
         self.scratch = None
         self.pass_events = []
@@ -550,6 +558,12 @@ class SlabPipeline:
             e1.record()
             self.pass_events.append((k, e0, e1))
 
+    def slab_start(self, n_slab_steps):
+        """State buffer the slab phase must start from so that the FINAL pass writes into buffer len(plan.steps()) % 2 -- where
+        the signed distance lives when it aliases a state buffer (alias_sdf), and where the ordinary path's final pass writes."""
+        last_dst = len(self.plan.steps()) % 2
+        return (1 - last_dst + n_slab_steps - 1) % 2
+
     def cyclic_phase(self, targets, buf, record=False):
         """Seed extraction + every pass with k >= world in the z-cyclic layout (this rank's planes z = rank mod world as a
         dense buffer): no exchange, full-length z-lattice columns; then the transpose into z-slabs, hidden behind the last of
@@ -668,12 +682,12 @@ class SlabPipeline:
             return
         p_ = self.plan
         steps = self.steps
-        if self.cyclic and self.dma == "split":
-            cur = 0
+        if self.cyclic and self.dma:
+            steps = [k for k in self.steps if k < p_.world]
+            cur = self.slab_start(len(steps))
             self.cyclic_phase(self.peer_ext[cur], cur, record_passes)
             self.symm[cur].barrier(channel=0)          # every rank's planes have landed in every slab
             self._mark(record_passes, "transpose")
-            steps = [k for k in self.steps if k < p_.world]
         elif self.use_early:
             if self.peer:
                 self.peer_barrier(0)          # buffer 0 is about to become scratch: nobody may still be reading it
@@ -694,7 +708,7 @@ class SlabPipeline:
         else:
             self.seed()
             cur = 0
-        if not (self.cyclic and self.dma == "split"):
+        if not (self.cyclic and self.dma):
             self._mark(record_passes, "seed")
         if self.dma == "split":
             # the first pass's halos come from the early kernel's result: one ordinary push + barrier; every later exchange
@@ -714,11 +728,11 @@ class SlabPipeline:
             return
         overlap = self.dma == "push" and self.overlap_halo
         halos_ready = False
-        for idx, k in enumerate(self.steps):
+        for idx, k in enumerate(steps):
             if not halos_ready:
                 self.exchange(k, cur)
                 self._mark(record_passes, "exchange")
-            nxt = self.steps[idx + 1] if idx + 1 < len(self.steps) else None
+            nxt = steps[idx + 1] if idx + 1 < len(steps) else None
             if overlap and nxt is not None and 2 * nxt <= p_.T and k < p_.T:
                 self.flood_overlapped(k, nxt, cur, record=record_passes)    # leaves the next pass's halos in place
                 halos_ready = True
@@ -821,9 +835,10 @@ class LocalComm:
                 p.grid_full[q.plan.rank * w:(q.plan.rank + 1) * w].copy_(q.grid_slab)
         steps = R[0].steps
         if self.cyclic and all(p.cyclic for p in R):
-            for p in R:
-                p.cyclic_phase([q.ext[0] for q in R], 0)
             steps = [k for k in steps if k < len(R)]
+            start = R[0].slab_start(len(steps))
+            for p in R:
+                p.cyclic_phase([q.ext[start] for q in R], start)
         elif self.dist_early and R[0].use_early and (R[0].n // 8) % len(R) == 0:
             ptrs = [q.center(1).data_ptr() for q in R]       # all slabs on this GPU: the work-sharing early kernel, emulated
             for p in R:
@@ -831,7 +846,7 @@ class LocalComm:
         else:
             for p in R:
                 p.early() if p.use_early else p.seed()
-        cur = 0 if (self.cyclic and all(p.cyclic for p in R)) else (1 if R[0].use_early else 0)
+        cur = start if (self.cyclic and all(p.cyclic for p in R)) else (1 if R[0].use_early else 0)
         for k in steps:
             for p in R:                                   # every receive pulls from the sender's current centre
                 for t in p.plan.recvs(k):

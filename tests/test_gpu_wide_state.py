@@ -82,6 +82,29 @@ def test_wide_state_z_slabs(world, meshes, oracle, vpb, monkeypatch):
     assert np.array_equal(sdf.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_wide_state_z_cyclic_first_phase(world, meshes, oracle, vpb, monkeypatch):
+    """The z-cyclic multi-GPU path (multi.py: cyclic_phase) with the 64-bit seed state of grids above 1024^3 -- the kernels
+    BASELINE config 5 (2048^3 on 8 GPUs) runs -- emulated on one GPU at a size the oracle checks."""
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    from cuda_mesh_voxelization_b200.multi import LocalComm, SlabPipeline
+    monkeypatch.setenv("VPB_JFA_STATE64", "1")
+    n = 128
+    names = ["bimba", "bunny"]
+    origin, vs = oracle.frame(np.concatenate([meshes[m][0] for m in names]), n)
+    dm = [DeviceMesh(*meshes[m], "cuda:0") for m in names]
+    comm = LocalComm(cyclic=True)
+    for r in range(world):
+        comm.add(SlabPipeline(n, vs, origin, r, world, comm=comm))
+    assert comm.ranks[0].esz == 8 and all(p.cyclic for p in comm.ranks)
+    sdf = comm.run_all(dm, op=capi.OP_DIFFERENCE)
+    torch.cuda.synchronize()
+    want = oracle.csg(oracle.voxelize(*meshes["bimba"], n, vs, origin), oracle.voxelize(*meshes["bunny"], n, vs, origin), n, 3)
+    assert np.array_equal(sdf.view(np.uint32), oracle.jfa(want, n, vs, origin).view(np.uint32))
+
+
 def _need_gib(gib):
     import torch
     torch.cuda.empty_cache()
