@@ -43,6 +43,7 @@ void usage() {
                 "  -b, --block-size arg  Accepted for compatibility, unused (default: 32)\n"
                 "  -m, --benckmark arg   Number of iteration in benckmark mode (default: 1)\n"
                 "      --fused           One device-resident pipeline call instead of one call per stage\n"
+                "      --gpus arg        Must be 1 here; several GPUs: one process per GPU, see INTEGRATION.md section D (default: 1)\n"
                 "  -h, --help            Print usage\n");
 }
 
@@ -130,6 +131,9 @@ int main(int argc, char** argv) {
     // benchmark mode folds grids[0] with an EMPTY grid per iteration (main.cpp:89,126-127,188); the fused call has no such
     // operand, so the [B200CSG] lines tools/benchmarks.py parses would silently disappear: refuse the combination
     cpuAssert(!(opt.fused && opt.iterations > 1), "--fused cannot be combined with -m (benchmark mode times the stages one by one)");
+    // the C ABI drives ONE device per process (vplib's own model); the multi-GPU slab driver is one process per GPU above it
+    cpuAssert(opt.gpus == 1, "--gpus > 1: run the z-slab driver, one process per GPU (INTEGRATION.md section D: "
+                             "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N, or multi.SlabPipeline.run_host)");
     cpuAssert(opt.type == static_cast<int>(Types::B200),
               "this build only contains the B200 back-end: use -t 4 (the reference's -t 0..3 live in the reference build)");
 
