@@ -247,6 +247,69 @@ def extra_run(args, n, op_name, rank, world, dev, barrier, steps=3, warmup=2):
     return rec
 
 
+def config4_run(args, rank, world, dev, barrier, steps=5, warmup=2):
+    """BASELINE config 4 beside the metric run: the bunny subdivided to 10 785 024 faces, solid AND (conservative) surface
+    voxelization at 1024^3, one z-slab per GPU -- both stages shard without any communication, so this is
+    launch- and set-up-bound and does not scale like the JFA (every rank still reads the whole mesh).  ms per step = max over
+    ranks of the CUDA-event time; the two popcounts summed over the ranks identify the result (equal at every N)."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from cuda_mesh_voxelization_b200 import capi, meshgen, shared_frame
+    from cuda_mesh_voxelization_b200.device import DeviceMesh
+    n, faces = 1024, 10785024
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    v, t = meshgen.bunny_with_faces(z["bunny_v"], z["bunny_t"], faces)
+    origin, vs = shared_frame([v], n)
+    lib = capi.load()
+    m = DeviceMesh(v, t, dev)
+    T = n // world
+    z0, z1 = rank * T, (rank + 1) * T
+    words = n * n * T // 32
+    solid = torch.empty(words, dtype=torch.int32, device=dev)
+    surf = torch.empty(words, dtype=torch.int32, device=dev)
+    need = max(int(lib.vpb_voxelize_scratch_bytes(n, m.n_tris, z0, z1)), int(lib.vpb_voxelize_surface_scratch_bytes(m.n_tris)), 16)
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    o = np.ascontiguousarray(origin, np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    from cuda_mesh_voxelization_b200.device import _stream
+    st = _stream()       # torch's current stream (the legacy default stream as cudaStreamLegacy, not 0 = the library's own)
+
+    def step():
+        capi.check(lib.vpb_voxelize_dev(ctypes.c_void_p(m.verts.data_ptr()), m.n_verts, ctypes.c_void_p(m.tris.data_ptr()), m.n_tris, n,
+                                        float(vs), o, z0, z1, ctypes.c_void_p(solid.data_ptr()), ctypes.c_void_p(scratch.data_ptr()),
+                                        scratch.numel(), st))
+        capi.check(lib.vpb_voxelize_surface_dev(ctypes.c_void_p(m.verts.data_ptr()), m.n_verts, ctypes.c_void_p(m.tris.data_ptr()),
+                                                m.n_tris, n, float(vs), o, z0, z1, ctypes.c_void_p(surf.data_ptr()),
+                                                ctypes.c_void_p(scratch.data_ptr()), scratch.numel(), st))
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+
+    def popcount(w):
+        b = w.view(torch.uint8).to(torch.int64)
+        return sum(((b >> i) & 1).sum() for i in range(8)).reshape(1)
+
+    counts = torch.cat([popcount(solid), popcount(surf)])
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts)
+    ms_step = float(ms.item()) / steps
+    del m, solid, surf, scratch
+    torch.cuda.empty_cache()
+    return {"workload": f"bunny subdivided to {faces} faces, solid + conservative surface voxelization at {n}^3 (BASELINE config 4), "
+                        f"{world} z-slab(s), no communication", "n": n, "faces": faces, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "value": n ** 3 / (ms_step * 1e-3) / 1e9, "unit": "Gvoxels/s (voxelization only)",
+            "solid_voxels": int(counts[0].item()), "surface_voxels": int(counts[1].item())}
+
+
 def golden_parity(args, digest):
     """Compares the run's sdf digests with the reference-generated ones (tests/golden/ref_digests_large.json, made by
     tests/golden/make_golden_large.py from the unmodified reference's OpenMP JFA).  "green" = every z-chunk of the final
@@ -476,6 +539,11 @@ def run_ours(args):
         del pipe
         torch.cuda.empty_cache()
         extra_runs = [extra_run(args, 2048, "difference", rank, world, dev, barrier)]
+    if args.config4 == "on" or (args.config4 == "auto" and n == 1024 and not replicas):
+        if extra_runs is None:
+            pipe = None
+            torch.cuda.empty_cache()
+        extra_runs = (extra_runs or []) + [config4_run(args, rank, world, dev, barrier)]
 
     if rank != 0:
         if world > 1:
@@ -546,6 +614,9 @@ def main():
     ap.add_argument("--seq-n", type=int, default=256, help="grid side of the one -t 0 (sequential) CPU step timed beside "
                     "the OpenMP one in cpu_baseline (0 = skip; 256^3 is ~15-20 s on one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config4", default="auto", choices=["auto", "on", "off"],
+                    help="also time BASELINE config 4 (10.8 M faces, solid + surface voxelization at 1024^3, z-slabs) and report it "
+                         "under config.extra_runs; auto = with the 1024^3 metric run")
     ap.add_argument("--extra-2048", default="auto", choices=["auto", "on", "off"],
                     help="also time BASELINE config 5 (difference + SDF at 2048^3) and report it under config.extra_runs; auto = "
                          "when 8 GPUs run the default 1024^3 workload")
