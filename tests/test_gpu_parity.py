@@ -668,3 +668,61 @@ def test_csg_fused_with_seed_shell(n, oracle, vpb):
     # a shape the fused kernel does not take
     assert lib.vpb_csg_shell_dev(ctypes.c_void_p(ta.data_ptr()), ctypes.c_void_p(tb.data_ptr()), 33, 1,
                                  ctypes.c_void_p(tc.data_ptr()), ctypes.c_void_p(ts.data_ptr()), ctypes.c_void_p(1)) == 1
+
+
+@pytest.mark.parametrize("res_step", [2, 4])
+def test_pass_parts_equal_the_whole_pass(res_step, meshes, oracle, vpb):
+    """vpb_jfa_pass_part_dev: the launches over the z residues 0 .. res_step-1 (the parity split of the multi-GPU driver for
+    res_step = 2) together write exactly what ONE vpb_jfa_pass_dev launch writes, for every step that has such residues."""
+    import ctypes
+    import torch
+    from cuda_mesh_voxelization_b200 import capi
+    from cuda_mesh_voxelization_b200.device import DeviceMesh, DevicePipeline
+    n = 256
+    names = ["bimba", "bunny"]
+    origin, vs = _frame(oracle, meshes, names, n)
+    pipe = DevicePipeline(n, vs, origin)
+    lib = pipe.lib
+    for i, m in enumerate(names):
+        pipe.voxelize(DeviceMesh(*meshes[m], "cuda:0"), pipe.grid_a if i == 0 else pipe.grid_b)
+    pipe.csg(capi.OP_UNION)
+    st = ctypes.c_void_p(1)
+    assert lib.vpb_jfa_early_dev(ctypes.c_void_p(pipe.grid_a.data_ptr()), n, 0, n, pipe.vs, pipe._o(),
+                                 ctypes.c_void_p(pipe.state_a.data_ptr()), ctypes.c_void_p(pipe.state_b.data_ptr()), st) == 0
+    src = pipe.state_b
+    whole = torch.empty_like(src)
+    parts = torch.empty_like(src)
+    plane_bytes = n * n * 4
+    for k in (16, 8, 4):
+        base = src.data_ptr()
+        capi.check(lib.vpb_jfa_pass_dev(ctypes.c_void_p(base - k * plane_bytes), ctypes.c_void_p(base), ctypes.c_void_p(base + k * plane_bytes),
+                                        ctypes.c_void_p(whole.data_ptr()), n, 0, n, k, pipe.vs, pipe._o(), None, None, None, st))
+        parts.fill_(-1)
+        for off in range(res_step):
+            assert lib.vpb_jfa_pass_part_dev(ctypes.c_void_p(base), ctypes.c_void_p(parts.data_ptr()), n, 0, n, k, pipe.vs, pipe._o(),
+                                             res_step, off, st) == 0
+            torch.cuda.synchronize()
+            # the launch wrote its own planes only
+            touched = (parts.view(n, n * n) != -1).any(dim=1).cpu().numpy()
+            assert np.array_equal(np.nonzero(touched)[0] % res_step <= off, np.ones(int(touched.sum()), bool))
+        torch.cuda.synchronize()
+        assert torch.equal(whole, parts), k
+        src, whole = whole, src            # next step from this result
+
+
+def test_copy_planes_strided(vpb):
+    """vpb_copy_planes_dev: n_planes pieces, separate strides on both sides (halo planes of one parity; cyclic -> slab transpose)."""
+    import ctypes
+    import torch
+    lib = vpb.load()
+    plane, cnt = 4096, 7
+    a = torch.arange(plane * cnt * 3 // 4, dtype=torch.int32, device="cuda")
+    b = torch.full((plane * cnt * 5 // 4,), -1, dtype=torch.int32, device="cuda")
+    assert lib.vpb_copy_planes_dev(ctypes.c_void_p(b.data_ptr() + 2 * plane), 5 * plane, ctypes.c_void_p(a.data_ptr() + plane), 3 * plane,
+                                   plane, cnt, ctypes.c_void_p(1)) == 0
+    torch.cuda.synchronize()
+    av, bv = a.view(cnt, 3, plane // 4), b.view(cnt, 5, plane // 4)
+    assert torch.equal(bv[:, 2], av[:, 1])
+    bv[:, 2] = -1
+    assert bool((b == -1).all())
+
