@@ -102,6 +102,23 @@ class SlabPlan:
         return out
 
 
+def cyclic_pieces(rank: int, world: int, T: int) -> List[Tuple[int, int, int, int, int]]:
+    """z-cyclic layout -> z-slabs, as seen by `rank` (which holds the planes z = rank mod world as a dense buffer, plane z at
+    index z // world).  One piece per destination d, in the order the pieces are produced and sent (own slab last, every
+    rank starting with another destination): (d, first cyclic plane, planes, first slab-local plane at d, plane stride at d)."""
+    tc = T // world
+    return [(d, d * tc, tc, rank, world) for d in [(rank + 1 + i) % world for i in range(world)]]
+
+
+def parity_boundary(T: int, nxt: int, q: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+    """Planes of parity q among the lowest and among the highest `nxt` planes of a slab of T planes (T even): the halo planes
+    the parity-q launch of a pass produces for the next pass (step nxt).  ((first, count) low, (first, count) high), stride 2."""
+    low = range(q, nxt, 2)
+    first_hi = T - nxt + ((T - nxt + q) % 2)
+    high = range(first_hi, T, 2)
+    return (q, len(low)), (first_hi, len(high))
+
+
 def slabs_for(n: int, world: int) -> int:
     """How many z-slabs a job of side n should be cut into on `world` GPUs (last row): grids up to
     512^3 stay on ONE GPU -- a 512^3 step is ~8 ms of kernels, less than the per-pass barriers and halo copies of a
@@ -533,15 +550,12 @@ class SlabPipeline:
             if record and self.trace is not None:
                 self.trace.append((k, q, t0, t1, done))
             # planes of parity q among [0, nxt) -> lower neighbour's upper halo, among [T - nxt, T) -> upper neighbour's lower halo
-            cnt = (nxt - q + 1) // 2 if nxt > q else 0       # p.T and T - nxt... are even for nxt >= 2; nxt == 1: plane 0 / T-1
+            (lo_first, lo_cnt), (hi_first, hi_cnt) = parity_boundary(p.T, nxt, q)
             jobs = []
             if p.rank > 0:
-                first = q                                    # first plane of parity q in [0, nxt)
-                jobs.append((p.rank - 1, first, (p.H + p.T + first), cnt, self.CH_LOW + q))
+                jobs.append((p.rank - 1, lo_first, (p.H + p.T + lo_first), lo_cnt, self.CH_LOW + q))
             if p.rank + 1 < p.world:
-                first = p.T - nxt + ((p.T - nxt + q) % 2)    # first plane of parity q in [T - nxt, T)
-                c_hi = len(range(first, p.T, 2))
-                jobs.append((p.rank + 1, first, (p.H - p.T + first), c_hi, self.CH_HIGH + q))
+                jobs.append((p.rank + 1, hi_first, (p.H - p.T + hi_first), hi_cnt, self.CH_HIGH + q))
             for side, (nb, first, at, c, ch) in enumerate(jobs):
                 st = self.side[side]
                 st.wait_event(done)
@@ -598,9 +612,10 @@ class SlabPipeline:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            parts = [((p.rank + 1 + i) % W) for i in range(W)] if last else [None]
-            for i, d in enumerate(parts):
-                lo, hi = (0, p.T) if d is None else (d * tc, (d + 1) * tc)
+            parts = cyclic_pieces(p.rank, W, p.T) if last else [None]
+            for i, piece in enumerate(parts):
+                d = None if piece is None else piece[0]
+                lo, hi = (0, p.T) if piece is None else (piece[1], piece[1] + piece[2])
                 rc = self.lib.vpb_jfa_pass_cyclic_dev(_ptr(self.cyc[c]), _ptr(self.cyc[1 - c]), n, W, p.rank, k, lo, hi, self.vs,
                                                       self._o(), self._stream())
                 if rc != 0:
@@ -612,9 +627,10 @@ class SlabPipeline:
                 st = self.tstreams[i % len(self.tstreams)]
                 st.wait_event(done)
                 used.append(st)
+                _, src_first, count, dst_first, dst_stride = piece
                 self.capi.check(self.lib.vpb_copy_planes_dev(
-                    ctypes.c_void_p(targets[d].data_ptr() + (p.H + p.rank) * pb), W * pb,
-                    ctypes.c_void_p(self.cyc[1 - c].data_ptr() + d * tc * pb), pb, pb, tc, ctypes.c_void_p(st.cuda_stream)))
+                    ctypes.c_void_p(targets[d].data_ptr() + (p.H + dst_first) * pb), dst_stride * pb,
+                    ctypes.c_void_p(self.cyc[1 - c].data_ptr() + src_first * pb), pb, pb, count, ctypes.c_void_p(st.cuda_stream)))
             if record:
                 e1.record()
                 self.pass_events.append((k, e0, e1))

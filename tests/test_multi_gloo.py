@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cuda_mesh_voxelization_b200.multi import SlabPlan
+from cuda_mesh_voxelization_b200.multi import SlabPlan, cyclic_pieces, parity_boundary
 
 
 def _free_port():
@@ -84,3 +84,60 @@ def test_plan_is_symmetric_and_complete():
 def test_bad_partition_is_rejected():
     with pytest.raises(ValueError):
         SlabPlan(100, 0, 3)
+
+
+def _cyclic_worker(rank, world, n, port, plane_elems):
+    """z-cyclic layout -> z-slabs: every rank holds the planes z = rank (mod world), sends the pieces cyclic_pieces() names and
+    must end up with exactly the planes of its slab, in order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = n // world
+        cyc = torch.arange(rank, n, world, dtype=torch.int32)[:, None].repeat(1, plane_elems)       # plane z holds the value z
+        slab = torch.full((T, plane_elems), -1, dtype=torch.int32)
+        ops, landing = [], []
+        for d, src_first, count, dst_first, dst_stride in cyclic_pieces(rank, world, T):
+            piece = cyc[src_first:src_first + count].clone()
+            if d == rank:
+                slab[dst_first::dst_stride][:count] = piece
+            else:
+                ops.append(dist.P2POp(dist.isend, piece, d))
+        for src in range(world):
+            if src == rank:
+                continue
+            # what rank `src` sends me: its piece for destination `rank`
+            (_, _, count, dst_first, dst_stride), = [x for x in cyclic_pieces(src, world, T) if x[0] == rank]
+            buf = torch.empty((count, plane_elems), dtype=torch.int32)
+            landing.append((buf, dst_first, dst_stride, count))
+            ops.append(dist.P2POp(dist.irecv, buf, src))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for buf, dst_first, dst_stride, count in landing:
+            slab[dst_first::dst_stride][:count] = buf
+        want = torch.arange(rank * T, (rank + 1) * T, dtype=torch.int32)[:, None].repeat(1, plane_elems)
+        assert torch.equal(slab, want), (rank, slab[:, 0].tolist())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 16), (4, 64), (8, 128)])
+def test_cyclic_to_slab_transpose_over_gloo(world, n):
+    mp.spawn(_cyclic_worker, args=(world, n, _free_port(), 4), nprocs=world, join=True)
+
+
+def test_parity_boundary_planes_cover_the_halos():
+    """The two parity launches of a pass together push exactly the nxt lowest and the nxt highest planes of the slab."""
+    for T in (16, 128, 512):
+        for nxt in (1, 2, 4, 8):
+            low, high = set(), set()
+            for q in (0, 1):
+                (lf, lc), (hf, hc) = parity_boundary(T, nxt, q)
+                lo_planes, hi_planes = set(range(lf, lf + 2 * lc, 2)), set(range(hf, hf + 2 * hc, 2))
+                assert all(z % 2 == q for z in lo_planes | hi_planes)
+                assert not (low & lo_planes) and not (high & hi_planes)
+                low |= lo_planes
+                high |= hi_planes
+            assert low == set(range(nxt)) and high == set(range(T - nxt, T)), (T, nxt, low, high)
+
