@@ -133,9 +133,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 constexpr int M_ALL = 0, M_FIRST = 1, M_LAST = 2;
 template <int M> struct Mode { static constexpr int value = M; };
 
+// Scalar instead of packed candidate arithmetic (experiment, measured and rejected: profiles/r02_flood5_notes.md section 4):
+// stride 1 only (VPB_F5_SCALAR1=1) or every stride up to VPB_F5_SCALAR_UPTO.
+#ifndef VPB_F5_SCALAR1
+#define VPB_F5_SCALAR1 0
+#endif
+#ifndef VPB_F5_SCALAR_UPTO
+#define VPB_F5_SCALAR_UPTO 0
+#endif
+
 template <int SS, int TR, int RPT, bool FINAL>
 struct Flood5 {
     using C = Cfg<SS, TR, RPT>;
+
+    // Candidate arithmetic on a pair of x-adjacent voxels: packed FADD2 / FFMA2.  For k = 1 the candidate columns x0-1 | x0 and
+    // x0+1 | x0+2 straddle the aligned pairs the window is loaded in and are re-paired with moves; the scalar forms (same
+    // roundings, no pairing, 18 fewer registers) nevertheless run SLOWER: 8.15 against 7.97 ms at k = 1, and +17 % per pass
+    // when every stride uses them -- twice the FP instructions cost more issue slots than the moves and the packed forms.
+    static constexpr bool SCALAR = (SS == 1 && VPB_F5_SCALAR1) || (SS <= VPB_F5_SCALAR_UPTO);
+    static __device__ __forceinline__ float2 add2(float2 a, float2 b) {
+        if (SCALAR) return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+        return __fadd2_rn(a, b);
+    }
+    static __device__ __forceinline__ float2 sqr2(float2 x, float2 nz) {
+        if (SCALAR) return make_float2(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        return sq2(x, nz);
+    }
 
     // the three candidate columns of one staged row, for the thread's two x-adjacent voxels
     static __device__ __forceinline__ void load_row(const float* p, float2 (&o)[3]) {
@@ -326,20 +349,20 @@ struct Flood5 {
                     uint32_t kk[RPT][3][3][2];   // [row][target][column][voxel] (only rows rho-2..rho are live)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float2 X = sq2(__fadd2_rn(fx[c], nqx), nz);          // (sx - qx)^2, shared by the rows
+                        const float2 X = sqr2(add2(fx[c], nqx), nz);          // (sx - qx)^2, shared by the rows
                         float2 Z[3];
 #pragma unroll
                         for (int t = 0; t < 3; ++t)
-                            if (TT[t]) Z[t] = sq2(__fadd2_rn(fz[c], nq[t]), nz);   // shared by the rows
+                            if (TT[t]) Z[t] = sqr2(add2(fz[c], nq[t]), nz);   // shared by the rows
 #pragma unroll
                         for (int r2 = 0; r2 < RPT; ++r2) {
                             const int r = rho - r2;                 // candidate row relative to voxel row r2
                             if (r < 0 || r > 2) continue;
-                            const float2 xy = __fadd2_rn(X, sq2(__fadd2_rn(fy[c], nqy[r2]), nz));
+                            const float2 xy = add2(X, sqr2(add2(fy[c], nqy[r2]), nz));
 #pragma unroll
                             for (int t = 0; t < 3; ++t) {
                                 if (!TT[t]) continue;
-                                const float2 d = __fadd2_rn(xy, Z[t]);   // ((dx*dx)+(dy*dy)) + (dz*dz)
+                                const float2 d = add2(xy, Z[t]);   // ((dx*dx)+(dy*dy)) + (dz*dz)
                                 const bool own = t == 1 && r == 1 && c == 1;
                                 const uint32_t kc = KEY_K0 + (own ? 0u : (uint32_t)(1 + r * 4 + c));
                                 uint32_t k0 = __float_as_uint(d.x) * 16u + kc, k1 = __float_as_uint(d.y) * 16u + kc;

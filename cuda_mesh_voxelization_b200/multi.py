@@ -281,6 +281,19 @@ class SlabPipeline:
         self.peer_ext = [[h.get_buffer(r, (total,), torch.int32) if r != p.rank else self.ext[i] for r in range(p.world)]
                          for i, h in enumerate(self.symm)]
         import os
+        # the occupancy grid in symmetric memory too: every rank writes its slab of bits straight into every other rank's grid
+        # with copy engines (gather_occupancy) instead of an NCCL all-gather (0.35 -> 0.2 ms on 8 GPUs at 1024^3)
+        self.peer_grid = None
+        if os.environ.get("VPB_GATHER", "push") != "nccl":
+            nw = self.grid_full.numel()
+            g = symm_mem.empty(nw, dtype=torch.int32, device=self.device)
+            g.zero_()
+            self.symm_grid = symm_mem.rendezvous(g, dist.group.WORLD)
+            wslab = nw // p.world
+            self.grid_full = g
+            self.grid_slab = g[p.rank * wslab:(p.rank + 1) * wslab]
+            self.peer_grid = [self.symm_grid.get_buffer(r, (nw,), torch.int32) if r != p.rank else g for r in range(p.world)]
+            self.gstreams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(min(4, p.world - 1))]
         # the fused early kernel in work-sharing form (each rank 1/world of the lattices, results stored straight into the
         # owners' slabs over NVLink) needs the slabs mapped everywhere, i.e. this mode; VPB_EARLY_DIST=0 turns it off
         self.dist_early = (self.use_early and (self.n // 8) % p.world == 0 and os.environ.get("VPB_EARLY_DIST", "1") != "0")
@@ -344,6 +357,25 @@ class SlabPipeline:
             return
         if self.comm is not None:
             self.comm.all_gather_bits(self)
+        elif getattr(self, "peer_grid", None) is not None:
+            # my slab of bits -> the same place in every other rank's grid, by copy engines over NVLink, then a barrier.  A peer
+            # may still be in the previous step's final pass, which reads only ITS OWN slab of its grid (the sign), never mine.
+            torch, p = self.torch, self.plan
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            w = self.grid_slab.numel()
+            for st in self.gstreams:
+                st.wait_event(ready)
+            for i in range(1, p.world):
+                d = (p.rank + i) % p.world
+                with torch.cuda.stream(self.gstreams[(i - 1) % len(self.gstreams)]):
+                    self.peer_grid[d][p.rank * w:(p.rank + 1) * w].copy_(self.grid_slab, non_blocking=True)
+            for st in self.gstreams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+            self.symm_grid.barrier(channel=0)
         else:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.grid_full, self.grid_slab.clone())
