@@ -1,34 +1,35 @@
-"""z-slab multi-GPU driver: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+"""Multi-GPU driver: one process per GPU, torch.distributed for the plumbing, symmetric memory over NVLink for the data.
 
-Partition.  Rank r owns the planes z in [r*T, (r+1)*T), T = N / world.
-  * voxelization / CSG : the fill axis is +X and rows are x-contiguous, so a z-slab owns whole rows — no parity
-                         carry, no communication.  Every rank rasterises the full mesh clipped to its slab.
-  * occupancy          : all-gathered once (N^3/8 bytes in total) — seed extraction needs one plane either side
-                         and the final pass needs the sign; the bit grid is tiny next to the seed state.
-  * first three passes : k = N/2, N/4, N/8 couple only voxels that are equal mod N/8, so every rank runs them for its own
-                         planes from the (all-gathered) occupancy bits in ONE kernel with no exchange at all
-                         (vpb_jfa_early_dev; each rank walks every 8x8x8 lattice and keeps the planes of its slab).
-  * JFA passes         : one halo exchange per remaining pass.  A voxel at z needs planes z-k and z+k:
-        k <  T : k boundary planes from each adjacent rank, received straight into the halo region of an
-                 extended buffer [T/2 | T | T/2 planes] so the pass kernel sees one contiguous z range;
-        k >= T : the whole slab of rank r -/+ k/T (NVSwitch: any peer at full bandwidth), received into two
-                 separate slab buffers (the pass kernel takes three independent plane pointers).
-  * halo transport     : by default the two extended state buffers live in torch symmetric memory (every rank's buffer is
-    mapped into every process over NVLink) and a rank PULLS the k boundary planes of each neighbour with one
-    copy-engine memcpy per neighbour straight into its own halo region, after a device-side barrier that says
-    "everyone's previous pass is complete" (`_setup_dma`, `exchange`).  No SMs are spent on the transfer and there is no
-    rendezvous per message: measured 8 x B200, 1024^3: halo time per step 4.1 ms (NCCL send/recv) -> see DESIGN.md §6.
-    VPB_HALO=nccl (or no symmetric-memory support) falls back to batched ncclSend/ncclRecv into the same halo regions.
-  * peer mode (opt-in: VPB_PEER=1 or peer=True): the two state buffers live in torch symmetric memory, every rank's
-    slab is mapped into every process over NVLink, and the pass kernel (vpb_jfa_pass_peer_dev) loads the planes
-    z-k / z+k it needs straight from the owning GPU while it computes — no halo copies at all, one device-side
-    barrier between passes.  Measured on 4 x B200 at 1024^3: 73 ms/step against 63 ms with the NCCL exchange (the
-    kernel's remote plane loads are latency-bound over NVLink), so the NCCL exchange stays the default.
-Results are bit-identical to the single-GPU pipeline by construction (same kernels, same candidate order).
+Partition.  Rank r of W owns the planes z in [r*T, (r+1)*T), T = N / W, of every RESULT; what happens on
+the way there (defaults on one 8 x B200 box; DESIGN.md section 6 has the measurements):
+  * voxelization / CSG : the fill axis is +X and rows are x-contiguous, so a z-slab owns whole rows -- no parity carry, no
+                         communication.  Every rank rasterises the full mesh clipped to its slab.
+  * occupancy          : gathered once (N^3/8 bytes in total): every rank writes its slab of bits straight into every other
+                         rank's grid (symmetric memory, copy engines), then one barrier.  Seed extraction needs a plane either
+                         side and the z-cyclic phase planes everywhere; the bit grid is tiny next to the seed state.
+  * z-cyclic phase     : (W >= 4) a pass with step k only couples planes that are equal mod k, so rank r keeps the planes
+                         z = r (mod W) as a dense buffer and runs the fused early kernel (exactly the lattices whose z residue
+                         is = r: all stores local) and every pass with k >= W there -- no exchange, full-length z-lattice
+                         columns (`cyclic_phase`, vpb_jfa_early_cyclic_dev / vpb_jfa_pass_cyclic_dev).  The last of these
+                         passes runs destination by destination and one strided copy-engine copy per destination
+                         (vpb_copy_planes_dev) transposes its planes into the owners' slabs while the next part is computed.
+  * slab passes        : the passes with k < W (all passes after the early kernel on 2 GPUs) need k boundary planes from each
+                         neighbour, received straight into the halo regions of an extended buffer [H | T | H planes] so that the
+                         kernel sees one contiguous z range.  PARITY SPLIT (`flood_split`, vpb_jfa_pass_part_dev): an even
+                         step does not couple even and odd planes, so a pass is two launches; when one is done copy engines
+                         push its boundary planes into the neighbours' halos and raise a flag in their signal pad, and the next
+                         pass's launch of that parity waits for the flags on the device.  No barrier per pass; the copies of
+                         one parity travel while the other is computed.
+  * 64-bit state (N > 1024): the z-cyclic phase as above (flood4 kernels), slab passes with one push + barrier per pass.
+  * fallbacks          : VPB_HALO=push|pull (copy-engine halos + one barrier per pass), VPB_HALO=nccl or no symmetric memory
+                         (batched ncclSend/ncclRecv into the same halo regions; k >= T: whole far slabs), VPB_CYCLIC=0,
+                         VPB_GATHER=nccl, VPB_PEER=1 (the pass kernel loads remote planes itself: measured slower).
+Results are bit-identical to the single-GPU pipeline by construction (same kernels, same candidate order) and are checked
+against the reference digests in every bench.py line and by tools/multi_gpu_check.py.
 
-The exchange *schedule* is pure Python (`SlabPlan`) and is exercised on CPU tensors over gloo in
-tests/test_multi_gloo.py; `SlabPipeline` runs it on GPUs.  `LocalComm` emulates the ranks inside one process
-(all slabs on one GPU) so the slab code paths are parity-tested on a single-GPU box as well.
+The exchange schedule and the index maps are pure Python (`SlabPlan`, `cyclic_pieces`, `parity_boundary`) and are exercised on
+CPU tensors over gloo in tests/test_multi_gloo.py; `SlabPipeline` runs them on GPUs.  `LocalComm` emulates the ranks inside
+one process (all slabs on one GPU) so the slab and z-cyclic code paths are parity-tested on a single-GPU box as well.
 """
 from __future__ import annotations
 
