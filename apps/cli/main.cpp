@@ -6,12 +6,17 @@
 // JFA), same "[label]: X ms" lines and the same export file names as the reference.  `-t 4` (the default here)
 // selects Types::B200; the reference's own back-ends (-t 0..3) are not part of this build.
 // `--fused` runs the whole loop through one vpb_pipeline_host call (grids stay in HBM between stages).
+// `--gpus N` (N > 1) runs the whole loop as z-slabs on N GPUs, one worker process per GPU (RunSlabWorkers).
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <filesystem>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 #include <vplib_b200/vplib_b200.h>
 #include <vplib_b200/mesh_io.h>
@@ -43,7 +48,7 @@ void usage() {
                 "  -b, --block-size arg  Accepted for compatibility, unused (default: 32)\n"
                 "  -m, --benckmark arg   Number of iteration in benckmark mode (default: 1)\n"
                 "      --fused           One device-resident pipeline call instead of one call per stage\n"
-                "      --gpus arg        Must be 1 here; several GPUs: one process per GPU, see INTEGRATION.md section D (default: 1)\n"
+                "      --gpus arg        Number of GPUs: N > 1 runs the whole pipeline as z-slabs, one worker process per GPU (default: 1)\n"
                 "  -h, --help            Print usage\n");
 }
 
@@ -121,6 +126,60 @@ template <typename Func>
 void Fold(HostVoxelsGrid<gridType>& a, HostVoxelsGrid<gridType>& b, Func f) { CSG::Compute<Types::B200>(a, b, f); }
 }  // namespace
 
+// --gpus N: the job goes to N worker processes (one per GPU, started through torch.distributed.run) as raw little-endian
+// files in a temporary directory; every worker writes its z-slab of the occupancy words and of the sdf into the job's output
+// files, which are read back here.  VPB_PYTHON (default "python") and VPB_ROOT (default: two directories above this binary)
+// say where the interpreter and the cuda_mesh_voxelization_b200 package are.
+static bool RunSlabWorkers(int gpus, const std::vector<Mesh>& meshes, unsigned n, float voxelSize, const float origin[3], int op,
+                           uint32_t* words, float* sdf) {
+    namespace fs = std::filesystem;
+    std::error_code ec;
+    std::string root;
+    if (const char* r = std::getenv("VPB_ROOT")) root = r;
+    else root = fs::canonical("/proc/self/exe", ec).parent_path().parent_path().parent_path().string();
+    char tmpl[] = "/tmp/vpb_job_XXXXXX";
+    if (!mkdtemp(tmpl)) return false;
+    const std::string job = tmpl;
+    auto dump = [&](const std::string& name, const void* data, size_t bytes) {
+        std::FILE* f = std::fopen((job + "/" + name).c_str(), "wb");
+        if (!f) return false;
+        const bool ok = bytes == 0 || std::fwrite(data, 1, bytes, f) == bytes;
+        return std::fclose(f) == 0 && ok;
+    };
+    bool ok = true;
+    for (size_t i = 0; i < meshes.size() && ok; ++i) {
+        ok = dump("mesh" + std::to_string(i) + ".verts", meshes[i].Coords.data(), meshes[i].Coords.size() * sizeof(Position)) &&
+             dump("mesh" + std::to_string(i) + ".tris", meshes[i].FacesCoords.data(), meshes[i].FacesCoords.size() / 3 * 3 * sizeof(uint32_t));
+    }
+    const size_t nWords = ((size_t)n * n * n + 31) / 32, nVox = (size_t)n * n * n;
+    if (ok) { ok = dump("words.bin", nullptr, 0); fs::resize_file(job + "/words.bin", nWords * 4, ec); ok = ok && !ec; }
+    if (ok && sdf) { ok = dump("sdf.bin", nullptr, 0); fs::resize_file(job + "/sdf.bin", nVox * 4, ec); ok = ok && !ec; }
+    if (ok) {
+        const char* py = std::getenv("VPB_PYTHON");
+        char hex[4][64];
+        std::snprintf(hex[0], 64, "%a", (double)voxelSize);
+        for (int a = 0; a < 3; ++a) std::snprintf(hex[1 + a], 64, "%a", (double)origin[a]);
+        const int port = 29600 + (int)(getpid() % 1000);
+        std::string cmd = "PYTHONPATH='" + root + "':\"$PYTHONPATH\" " + (py ? py : "python") +
+                          " -m torch.distributed.run --nnodes=1 --nproc-per-node " + std::to_string(gpus) +
+                          " --master-addr 127.0.0.1 --master-port " + std::to_string(port) +
+                          " -m cuda_mesh_voxelization_b200.slab_worker '" + job + "' " + std::to_string(meshes.size()) + " " +
+                          std::to_string(n) + " " + hex[0] + " " + hex[1] + " " + hex[2] + " " + hex[3] + " " + std::to_string(op) +
+                          " " + (sdf ? "1" : "0") + " 1>&2";
+        ok = std::system(cmd.c_str()) == 0;
+    }
+    auto slurp = [&](const std::string& name, void* data, size_t bytes) {
+        std::FILE* f = std::fopen((job + "/" + name).c_str(), "rb");
+        if (!f) return false;
+        const bool got = std::fread(data, 1, bytes, f) == bytes;
+        std::fclose(f);
+        return got;
+    };
+    ok = ok && slurp("words.bin", words, nWords * 4) && (!sdf || slurp("sdf.bin", sdf, nVox * 4));
+    fs::remove_all(job, ec);
+    return ok;
+}
+
 int main(int argc, char** argv) {
     cpuAssert((argc >= 2), "Need [input file]\n");
     Options opt;
@@ -131,9 +190,10 @@ int main(int argc, char** argv) {
     // benchmark mode folds grids[0] with an EMPTY grid per iteration (main.cpp:89,126-127,188); the fused call has no such
     // operand, so the [B200CSG] lines tools/benchmarks.py parses would silently disappear: refuse the combination
     cpuAssert(!(opt.fused && opt.iterations > 1), "--fused cannot be combined with -m (benchmark mode times the stages one by one)");
-    // the C ABI drives ONE device per process (vplib's own model); the multi-GPU slab driver is one process per GPU above it
-    cpuAssert(opt.gpus == 1, "--gpus > 1: run the z-slab driver, one process per GPU (INTEGRATION.md section D: "
-                             "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N, or multi.SlabPipeline.run_host)");
+    // the C ABI drives ONE device per process (vplib's own model): --gpus N starts one worker process per GPU (the z-slab
+    // driver, cuda_mesh_voxelization_b200/slab_worker.py) for the whole pipeline, like --fused does in this process
+    cpuAssert(!(opt.gpus > 1 && opt.iterations > 1), "--gpus cannot be combined with -m (benchmark mode times the stages one by one)");
+    cpuAssert(!(opt.gpus > 1 && opt.numVoxels % (32 * opt.gpus) != 0), "--gpus N needs -n to be a multiple of 32 * N");
     cpuAssert(opt.type == static_cast<int>(Types::B200),
               "this build only contains the B200 back-end: use -t 4 (the reference's -t 0..3 live in the reference build)");
 
@@ -163,7 +223,15 @@ int main(int argc, char** argv) {
 
     for (unsigned j = 0; j < opt.iterations; ++j) {
         HostGrid<float> sdf;
-        if (opt.fused) {
+        if (opt.gpus > 1) {
+            VPB_PROFILING_SCOPE("B200Pipeline");
+            grids[0] = HostVoxelsGrid<gridType>(NUM_VOXELS, voxelSize);
+            grids[0].View().SetOrigin(originX, originY, originZ);
+            if (opt.sdf) sdf = HostGrid<float>(NUM_VOXELS, -INFINITY);
+            cpuAssert(RunSlabWorkers(opt.gpus, meshes, NUM_VOXELS, voxelSize, grids[0].Origin(), opt.operation,
+                                     grids[0].Words32(), opt.sdf ? sdf.Data() : nullptr),
+                      "the multi-GPU workers failed (python -m torch.distributed.run ... cuda_mesh_voxelization_b200.slab_worker)");
+        } else if (opt.fused) {
             // one call: every grid stays on the device between stages (include/vpb200.h: vpb_pipeline_host)
             VPB_PROFILING_SCOPE("B200Pipeline");
             vplib_b200::ensure_init();
@@ -218,7 +286,7 @@ int main(int argc, char** argv) {
         }
 
         if (opt.sdf) {
-            if (!opt.fused) {
+            if (!opt.fused && opt.gpus == 1) {
                 sdf = HostGrid<float>(grids[0].View().VoxelsPerSide(), -INFINITY);
                 JFA::Compute<Types::B200>(grids[0], sdf);
             }

@@ -59,6 +59,31 @@ def test_cli_union_sdf_matches_reference_digests(cli, fused, tmp_path, meshes, g
     assert int(pc[1].split()[-1]) == rec["result"]["popcount"]
 
 
+def test_cli_gpus_2_runs_the_slab_workers(cli, tmp_path, meshes, golden, oracle):
+    """--gpus 2: the CLI hands the job to two worker processes (cuda_mesh_voxelization_b200/slab_worker.py, one per GPU, z-slabs
+    with NVLink halos) and reads their slabs back: same digests and export files as the one-GPU run.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rec = golden["sphere_union_torus_n64"]
+    files = []
+    for m in rec["meshes"]:
+        p = tmp_path / f"{m}.obj"
+        write_obj(p, *meshes[m])
+        files.append(str(p))
+    (tmp_path / "out").mkdir()
+    env = dict(os.environ, VPB_CLI_DUMP=str(tmp_path / "dump"), VPB_ROOT=ROOT)
+    cmd = [cli, *files, "-n", "64", "-t", "4", "-p", "1", "-s", "-e", "-o", "res.obj", "--gpus", "2"]
+    out = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:] + out.stdout
+    bits = np.fromfile(tmp_path / "dump.bits", np.uint32)
+    sdf = np.fromfile(tmp_path / "dump.sdf", np.float32)
+    assert f"{oracle.fnv(bits):016x}" == rec["result"]["fnv"]
+    assert f"{oracle.fnv(sdf):016x}" == rec["sdf"]["fnv"]
+    for f in ["csg_vox_b200_res.obj", "sdf_b200_res.obj", "sdf_point_cloud_b200_res.obj"]:
+        assert os.path.getsize(tmp_path / "out" / f) > 100
+
+
 def test_cli_rejects_other_backends(cli, tmp_path, meshes):
     p = tmp_path / "d20.obj"
     write_obj(p, *meshes["d20"])
