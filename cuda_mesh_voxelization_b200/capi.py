@@ -51,6 +51,8 @@ SIGNATURES = [
     ("vpb_copy_planes_dev", ctypes.c_int, [_vp, ctypes.c_size_t, _vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _vp]),
     ("vpb_jfa_early_cyclic_dev", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_float, _f32p, ctypes.c_uint32, ctypes.c_uint32, _vp,
                                                 _vp, _vp]),
+    ("vpb_jfa_pass_cyclic_to_slab_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, _f32p, _vp]),
     ("vpb_jfa_pass_cyclic_dev", ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                                ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, _f32p, _vp]),
     ("vpb_jfa_state_bytes", ctypes.c_size_t, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),

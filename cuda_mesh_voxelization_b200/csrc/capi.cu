@@ -428,7 +428,7 @@ int vpb_jfa_pass_part_dev(const uint32_t* src_mid, uint32_t* dst, uint32_t n, ui
     VPB_REQUIRE(n > 0 && n <= kMaxJfaN && z0 < z1 && z1 <= n && k >= 1 && k < n, "jfa_pass_part: bad n=%u slab [%u,%u) k=%u", n, z0, z1, k);
     if (jfa_state64(n)) return 1;
     return jfa_pass_flood5_launch(src_mid, dst, make_frame(n, vs, origin), z0, z1, k, nullptr, nullptr, nullptr,
-                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, res_step, res_off, 1, 0);
+                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, res_step, res_off, 1, 0, 1, 0);
 }
 
 int vpb_copy_planes_dev(void* dst, size_t dst_stride, const void* src, size_t src_stride, size_t plane_bytes, size_t n_planes,
@@ -464,8 +464,21 @@ int vpb_jfa_pass_cyclic_dev(const uint32_t* src, uint32_t* dst, uint32_t n, uint
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream;
     if (jfa_state64(n)) return jfa_pass_flood4_cyclic_launch_s64(src, dst, f, plane_lo, plane_hi, k, world, rank, st);
     const size_t off = (size_t)plane_lo * n * n;
-    const int rc = jfa_pass_flood5_launch(src + off, dst + off, f, plane_lo, plane_hi, k, nullptr, nullptr, nullptr, st, 1, 0, world, rank);
+    const int rc = jfa_pass_flood5_launch(src + off, dst + off, f, plane_lo, plane_hi, k, nullptr, nullptr, nullptr, st, 1, 0, world, rank, 1, 0);
     return rc == 1 ? jfa_pass_flood4_cyclic_launch(src, dst, f, plane_lo, plane_hi, k, world, rank, st) : rc;
+}
+
+int vpb_jfa_pass_cyclic_to_slab_dev(const uint32_t* src, uint32_t* dst_slab, uint32_t n, uint32_t world, uint32_t rank, uint32_t k,
+                                    uint32_t plane_lo, uint32_t plane_hi, float vs, const float origin[3], void* stream) {
+    VPB_TRY(require_ready());
+    VPB_REQUIRE(origin && src && dst_slab, "jfa_pass_cyclic_to_slab: null argument");
+    VPB_REQUIRE(n > 0 && n <= kMaxJfaN && world >= 1 && rank < world && n % world == 0 && k >= 1 && k < n,
+                "jfa_pass_cyclic_to_slab: bad n=%u rank %u of %u k=%u", n, rank, world, k);
+    VPB_REQUIRE(plane_lo < plane_hi && plane_hi <= n / world, "jfa_pass_cyclic_to_slab: bad plane range [%u,%u) of %u", plane_lo, plane_hi, n / world);
+    if (jfa_state64(n) || k % world != 0) return 1;
+    const size_t off = (size_t)plane_lo * n * n;
+    return jfa_pass_flood5_launch(src + off, dst_slab, make_frame(n, vs, origin), plane_lo, plane_hi, k, nullptr, nullptr, nullptr,
+                                  stream ? static_cast<cudaStream_t>(stream) : g_ctx.stream, 1, 0, world, rank, world, rank);
 }
 
 int vpb_jfa_pass_peer_dev(const uint32_t* const* slab_states, uint32_t world, uint32_t slab_planes, uint32_t* dst,

@@ -152,7 +152,7 @@ int jfa_finalize_launch(const uint32_t* state, const Frame& f, uint32_t z0, uint
 // zl with zl % res_step == res_off.  1 = shape not taken.
 int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k,
                            const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t res_step,
-                           uint32_t res_off, uint32_t zmul, uint32_t zadd);
+                           uint32_t res_off, uint32_t zmul, uint32_t zadd, uint32_t out_mul, uint32_t out_add);
 // seed extraction + the passes k = N/2, N/4, N/8 in one kernel (jfa_early.cu); 1 = shape/frame not taken, caller runs them one by one
 int jfa_early_launch(const uint32_t* words_full, const Frame& f, uint32_t z0, uint32_t z1, uint32_t* shell_scratch,
                      uint32_t* state, cudaStream_t st);

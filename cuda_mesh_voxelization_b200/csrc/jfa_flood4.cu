@@ -30,7 +30,7 @@ int jfa_pass_flood3_launch(const uint32_t* below, const uint32_t* mid, const uin
 #define VPB_F4_FALLBACK jfa_pass_flood3_launch
 int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k,
                            const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t res_step,
-                           uint32_t res_off, uint32_t zmul, uint32_t zadd);                                     // jfa_flood5.cu (v5, TMA staging)
+                           uint32_t res_off, uint32_t zmul, uint32_t zadd, uint32_t out_mul, uint32_t out_add);                                     // jfa_flood5.cu (v5, TMA staging)
 #else
 int jfa_pass_gather_launch_s64(const state_t* below, const state_t* mid, const state_t* above, state_t* dst,
                                const Frame& f, uint32_t z0, uint32_t z1, uint32_t k, const uint32_t* words_full,
@@ -515,7 +515,7 @@ static int flood4_launch_impl(const state_t* below, const state_t* mid, const st
     {   // v5 (TMA-staged planes) takes the common case: source planes contiguous around the slab, >= 16 lattice rows
         const ptrdiff_t kp5 = (ptrdiff_t)k * n * n;
         if (!force3 && !cyclic && above == mid + kp5 && below == mid - kp5) {
-            const int rc = jfa_pass_flood5_launch(mid, dst, f, z0, z1, k, words_full, sdf, seeds, st, 1, 0, 1, 0);
+            const int rc = jfa_pass_flood5_launch(mid, dst, f, z0, z1, k, words_full, sdf, seeds, st, 1, 0, 1, 0, 1, 0);
             if (rc <= 0) return rc;
         }
     }

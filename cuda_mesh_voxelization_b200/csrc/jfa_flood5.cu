@@ -57,6 +57,7 @@ struct F5Args {
     int kz;                   // the same step in PLANES of the source / destination buffers (k, or k / zmul)
     int zmul, zadd;           // grid z of buffer plane zl (slab-local) = (zl + z0) * zmul + zadd   (1, 0 for a z-slab)
     int zn;                   // (zl + z0) in [0, zn) <=> the plane is inside the grid
+    int out_mul, out_add;     // output plane zl is stored at plane zl * out_mul + out_add of dst (1, 0: in place of its source plane)
     int zbias;                // tensor-map z coordinate of slab-local plane 0
     int lz, segs_z;           // outputs per march segment, segments per z-lattice column
     int res_z, cols;          // z-lattice columns this launch walks; consecutive columns walked by one CTA
@@ -411,7 +412,7 @@ struct Flood5 {
             }
             // ---- output plane p-1 is complete ---------------------------------------------------------------------
             if (T2 && p >= 1) {
-                const vox_t zoff = (vox_t)(zl0 + (p - 1) * kz) * plane_sz;
+                const vox_t zoff = (vox_t)((zl0 + (p - 1) * kz) * a.out_mul + a.out_add) * plane_sz;
                 // ring word offsets of the planes p-2 (N group), p-1 (C group), p (P group)
                 const uint32_t offN = (uint32_t)(((p - 1) & 3) * C::SLOT * 4), offC = (uint32_t)((p & 3) * C::SLOT * 4),
                                offP = (uint32_t)(((p + 1) & 3) * C::SLOT * 4);   // bytes
@@ -546,12 +547,15 @@ EncodeTiledFn encode_tiled() {
 // runs the even and the odd planes as two launches and moves the halo planes of one behind the other (multi.py).
 int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, uint32_t z0, uint32_t z1, uint32_t k,
                            const uint32_t* words_full, float* sdf, uint32_t* seeds, cudaStream_t st, uint32_t res_step,
-                           uint32_t res_off, uint32_t zmul, uint32_t zadd) {
+                           uint32_t res_off, uint32_t zmul, uint32_t zadd, uint32_t out_mul, uint32_t out_add) {
+    // out_mul / out_add: output plane zl (slab-local) lands at plane zl * out_mul + out_add of dst -- the cyclic -> slab
+    // transpose done by the kernel's own stores (dst may be a peer GPU's slab mapped over NVLink).  Not for the final pass.
     // zmul > 1: the buffers hold the planes z = zl * zmul + zadd of the grid (zl = 0 .. N / zmul - 1): the z-CYCLIC layout of
     // the multi-GPU driver, in which a pass whose step is a multiple of zmul needs no other rank's planes -- z +- k is the
     // buffer plane zl +- k / zmul.  x and y are stepped by k, the buffer by kz = k / zmul planes; [z0, z1) are buffer planes.
     const uint32_t n = f.n, T = z1 - z0;
     if (zmul == 0 || k % zmul != 0 || zadd >= zmul || n % zmul != 0 || (zmul > 1 && (z1 * zmul > n || sdf))) return 1;
+    if (out_mul == 0 || ((out_mul != 1 || out_add != 0) && sdf)) return 1;
     const uint32_t kz = k / zmul, zn = n / zmul;
     const char* env = getenv("VPB_JFA_KERNEL");
     if (env && strcmp(env, "flood5") != 0) return 1;
@@ -596,6 +600,7 @@ int jfa_pass_flood5_launch(const uint32_t* mid, uint32_t* dst, const Frame& f, u
     }
     a.n = n; a.z0 = z0; a.T = T; a.k = (int)k;
     a.kz = (int)kz; a.zmul = (int)zmul; a.zadd = (int)zadd; a.zn = (int)zn;
+    a.out_mul = (int)out_mul; a.out_add = (int)out_add;
     a.zbias = (int)below;
     a.neg_zero = -0.0f;
     a.glut = jfa_lut_launch(f, st);

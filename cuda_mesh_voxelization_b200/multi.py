@@ -174,12 +174,15 @@ class SlabPipeline:
         self.bit_plane = n * n
         # z-cyclic first phase (early kernel + the passes k >= world without any exchange, then one transpose into the
         # slabs): pays from 4 GPUs on, where thin slabs shorten the z-lattice columns of the large steps and the first halo
-        # exchange is the largest (profiles/r02_multi_gpu_notes.md).  VPB_CYCLIC=1 / 0 forces it on (from 2 ranks) / off.
+        # exchange is the largest, and on 2 GPUs as well once the kernel stores its own slab directly (profiles/r02_multi_gpu_notes.md).
+        # VPB_CYCLIC=1 / 0 forces it on / off.
         import os
         want_cyc = os.environ.get("VPB_CYCLIC", "auto")
         local_cyclic = comm is not None and getattr(comm, "cyclic", False)
         w = world
-        cyc_elig = bool(want_cyc != "0" and (w >= 4 or want_cyc == "1" or local_cyclic) and w >= 2 and (w & (w - 1)) == 0
+        # on 2 GPUs only with the 32-bit state: the kernel stores its own half straight into the slab (no 1 GB local copy), and
+        # four buffers of half a 64-bit 2048^3 state would not leave room for anything else
+        cyc_elig = bool(want_cyc != "0" and (w >= 4 or self.esz == 4 or want_cyc == "1" or local_cyclic) and w >= 2 and (w & (w - 1)) == 0
                         and self.use_early and n % 64 == 0 and (n // 8) % w == 0 and p.T % w == 0
                         and any(k < w for k in self.steps) and any(k >= w for k in self.steps)
                         and (comm is None or local_cyclic)
@@ -247,6 +250,7 @@ class SlabPipeline:
         else:
             self.sdf = torch.empty(self.slab_voxels, dtype=torch.float32, device=self.device)
         self.seeds = torch.empty(self.slab_voxels, **i32) if want_seeds else None
+        self.transpose = os.environ.get("VPB_TRANSPOSE", "own")     # copy | own | direct (cyclic_phase)
         if self.cyclic:
             self.cyc = [torch.empty(self.slab_voxels * self.w32, **i32) for _ in range(2)]
             self.tstreams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(4)]
@@ -649,11 +653,18 @@ class SlabPipeline:
             for i, piece in enumerate(parts):
                 d = None if piece is None else piece[0]
                 lo, hi = (0, p.T) if piece is None else (piece[1], piece[1] + piece[2])
-                rc = self.lib.vpb_jfa_pass_cyclic_dev(_ptr(self.cyc[c]), _ptr(self.cyc[1 - c]), n, W, p.rank, k, lo, hi, self.vs,
-                                                      self._o(), self._stream())
+                # the kernel's own stores do the transpose (vpb_jfa_pass_cyclic_to_slab_dev) for my own slab -- no local copy
+                # -- and, with VPB_TRANSPOSE=direct, for the peers' slabs too (stores over NVLink instead of copy engines)
+                direct = d is not None and self.esz == 4 and (self.transpose == "direct" or (self.transpose == "own" and d == p.rank))
+                if direct:
+                    rc = self.lib.vpb_jfa_pass_cyclic_to_slab_dev(_ptr(self.cyc[c]), ctypes.c_void_p(targets[d].data_ptr() + p.H * pb),
+                                                                  n, W, p.rank, k, lo, hi, self.vs, self._o(), self._stream())
+                else:
+                    rc = self.lib.vpb_jfa_pass_cyclic_dev(_ptr(self.cyc[c]), _ptr(self.cyc[1 - c]), n, W, p.rank, k, lo, hi, self.vs,
+                                                          self._o(), self._stream())
                 if rc != 0:
                     self.capi.check(rc if rc < 0 else -1)
-                if d is None:
+                if d is None or direct:
                     continue
                 done = torch.cuda.Event()
                 done.record(main)

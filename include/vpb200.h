@@ -195,6 +195,12 @@ VPB_API int vpb_jfa_early_cyclic_dev(const uint32_t* words_full, uint32_t n, flo
 VPB_API int vpb_jfa_pass_cyclic_dev(const uint32_t* src_cyclic, uint32_t* dst_cyclic, uint32_t n, uint32_t world, uint32_t rank,
                                     uint32_t k, uint32_t plane_lo, uint32_t plane_hi, float voxel_size, const float origin[3],
                                     void* stream);
+/* The same pass with the cyclic -> slab transpose done by the kernel's own stores: buffer plane plane_lo + j is written to
+ * plane j * world + rank of dst_slab -- the z-slab of the rank that owns the grid planes (plane_lo + j) * world + rank, which
+ * may be this GPU's or a peer's memory mapped over NVLink (full 128-byte lines per warp).  32-bit state only. */
+VPB_API int vpb_jfa_pass_cyclic_to_slab_dev(const uint32_t* src_cyclic, uint32_t* dst_slab, uint32_t n, uint32_t world,
+                                            uint32_t rank, uint32_t k, uint32_t plane_lo, uint32_t plane_hi, float voxel_size,
+                                            const float origin[3], void* stream);
 /* The same pass for multi-GPU runs WITHOUT halo copies: slab_states[r] (r < world <= 8) is the device address, valid in
  * THIS process, of rank r's slab of the source state (planes [r*slab_planes, (r+1)*slab_planes), slab_planes*world == N)
  * — the ranks' buffers mapped over NVLink (CUDA IPC / torch symmetric memory).  The kernel loads the planes z-k / z+k
