@@ -4,16 +4,17 @@ Partition.  Rank r of W owns the planes z in [r*T, (r+1)*T),
 the way there (defaults on one 8 x B200 box; DESIGN.md section 6 has the measurements):
   * voxelization / CSG : the fill axis is +X and rows are x-contiguous, so a z-slab owns whole rows -- no parity carry, no
                          communication.  Every rank rasterises the full mesh clipped to its slab.
-  * occupancy          : gathered once (N^3/8 bytes in total): every rank writes its slab of bits straight into every other
-                         rank's grid (symmetric memory, copy engines), then one barrier.  Seed extraction needs a plane either
-                         side and the z-cyclic phase planes everywhere; the bit grid is tiny next to the seed state.
-  * z-cyclic phase     : (W >= 4) a pass with step k only couples planes that are equal mod k, so rank r keeps the planes
+  * occupancy          : all-gathered once (N^3/8 bytes in total; NCCL, or VPB_GATHER=push: copy-engine writes into the peers'
+                         grids).  Seed extraction needs a plane either side and the z-cyclic phase planes everywhere; the bit
+                         grid is tiny next to the seed state.
+  * z-cyclic phase     : (32-bit state: W >= 2; 64-bit: W >= 4) a pass with step k only couples planes that are equal mod k, so rank r keeps the planes
                          z = r (mod W) as a dense buffer and runs the fused early kernel (exactly the lattices whose z residue
                          is = r: all stores local) and every pass with k >= W there -- no exchange, full-length z-lattice
                          columns (`cyclic_phase`, vpb_jfa_early_cyclic_dev / vpb_jfa_pass_cyclic_dev).  The last of these
-                         passes runs destination by destination and one strided copy-engine copy per destination
-                         (vpb_copy_planes_dev) transposes its planes into the owners' slabs while the next part is computed.
-  * slab passes        : the passes with k < W (all passes after the early kernel on 2 GPUs) need k boundary planes from each
+                         passes runs destination by destination: the part for the rank's own slab is stored there by the
+                         kernel itself (vpb_jfa_pass_cyclic_to_slab_dev), the others leave through one strided copy-engine copy
+                         per destination (vpb_copy_planes_dev) while the next part is computed.
+  * slab passes        : the passes with k < W need k boundary planes from each
                          neighbour, received straight into the halo regions of an extended buffer [H | T | H planes] so that the
                          kernel sees one contiguous z range.  PARITY SPLIT (`flood_split`, vpb_jfa_pass_part_dev): an even
                          step does not couple even and odd planes, so a pass is two launches; when one is done copy engines
@@ -286,10 +287,12 @@ class SlabPipeline:
         self.peer_ext = [[h.get_buffer(r, (total,), torch.int32) if r != p.rank else self.ext[i] for r in range(p.world)]
                          for i, h in enumerate(self.symm)]
         import os
-        # the occupancy grid in symmetric memory too: every rank writes its slab of bits straight into every other rank's grid
-        # with copy engines (gather_occupancy) instead of an NCCL all-gather (0.35 -> 0.2 ms on 8 GPUs at 1024^3)
+        # VPB_GATHER=push: the occupancy grid in symmetric memory too, every rank writes its slab of bits straight into every
+        # other rank's grid with copy engines (gather_occupancy) instead of the NCCL all-gather.  Measured on 8 GPUs: the same
+        # 0.3-0.45 ms at 1024^3 (the stage is mostly the ranks waiting for each other) and SLOWER at 2048^3 (2.1 against 1.6 ms:
+        # seven unicast copies per rank against NCCL's switch multicast), so the all-gather stays the default.
         self.peer_grid = None
-        if os.environ.get("VPB_GATHER", "push") != "nccl":
+        if os.environ.get("VPB_GATHER", "nccl") == "push":
             nw = self.grid_full.numel()
             g = symm_mem.empty(nw, dtype=torch.int32, device=self.device)
             g.zero_()
