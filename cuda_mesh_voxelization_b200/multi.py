@@ -255,6 +255,8 @@ class SlabPipeline:
         if self.cyclic:
             self.cyc = [torch.empty(self.slab_voxels * self.w32, **i32) for _ in range(2)]
             self.tstreams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(4)]
+            self.lstreams = ([torch.cuda.Stream(device=self.device) for _ in range(2)]
+                             if os.environ.get("VPB_CYCLIC_STREAMS", "2") != "1" and world >= 4 else [])
         self.scratch = None
         self.pass_events = []
         self.early_events = []
@@ -653,24 +655,34 @@ class SlabPipeline:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             parts = cyclic_pieces(p.rank, W, p.T) if last else [None]
+            # the parts of the last pass are small launches (N / W^2 planes: 2.3 waves of CTAs on 8 GPUs): they alternate
+            # between two streams so that the tail of one fills with the head of the next
+            fork = None
+            if last and self.lstreams:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                for ls in self.lstreams:
+                    ls.wait_event(fork)
             for i, piece in enumerate(parts):
                 d = None if piece is None else piece[0]
                 lo, hi = (0, p.T) if piece is None else (piece[1], piece[1] + piece[2])
+                ls = self.lstreams[i % len(self.lstreams)] if fork is not None else main
+                launch_stream = ctypes.c_void_p(ls.cuda_stream) if fork is not None else self._stream()
                 # the kernel's own stores do the transpose (vpb_jfa_pass_cyclic_to_slab_dev) for my own slab -- no local copy
                 # -- and, with VPB_TRANSPOSE=direct, for the peers' slabs too (stores over NVLink instead of copy engines)
                 direct = d is not None and self.esz == 4 and (self.transpose == "direct" or (self.transpose == "own" and d == p.rank))
                 if direct:
                     rc = self.lib.vpb_jfa_pass_cyclic_to_slab_dev(_ptr(self.cyc[c]), ctypes.c_void_p(targets[d].data_ptr() + p.H * pb),
-                                                                  n, W, p.rank, k, lo, hi, self.vs, self._o(), self._stream())
+                                                                  n, W, p.rank, k, lo, hi, self.vs, self._o(), launch_stream)
                 else:
                     rc = self.lib.vpb_jfa_pass_cyclic_dev(_ptr(self.cyc[c]), _ptr(self.cyc[1 - c]), n, W, p.rank, k, lo, hi, self.vs,
-                                                          self._o(), self._stream())
+                                                          self._o(), launch_stream)
                 if rc != 0:
                     self.capi.check(rc if rc < 0 else -1)
                 if d is None or direct:
                     continue
                 done = torch.cuda.Event()
-                done.record(main)
+                done.record(ls)
                 st = self.tstreams[i % len(self.tstreams)]
                 st.wait_event(done)
                 used.append(st)
@@ -678,6 +690,11 @@ class SlabPipeline:
                 self.capi.check(self.lib.vpb_copy_planes_dev(
                     ctypes.c_void_p(targets[d].data_ptr() + (p.H + dst_first) * pb), dst_stride * pb,
                     ctypes.c_void_p(self.cyc[1 - c].data_ptr() + src_first * pb), pb, pb, count, ctypes.c_void_p(st.cuda_stream)))
+            if fork is not None:
+                for ls in self.lstreams:
+                    ev = torch.cuda.Event()
+                    ev.record(ls)
+                    main.wait_event(ev)
             if record:
                 e1.record()
                 self.pass_events.append((k, e0, e1))
