@@ -136,6 +136,10 @@ template <int M> struct Mode { static constexpr int value = M; };
 
 // Scalar instead of packed candidate arithmetic (experiment, measured and rejected: profiles/r02_flood5_notes.md section 4):
 // stride 1 only (VPB_F5_SCALAR1=1) or every stride up to VPB_F5_SCALAR_UPTO.
+// CTAs per SM the two-row form is compiled for at strides <= 8 (where three 64 KB CTAs fit in shared memory): experiment
+#ifndef VPB_F5_CTAS_R2_SMALL
+#define VPB_F5_CTAS_R2_SMALL 2
+#endif
 #ifndef VPB_F5_SCALAR1
 #define VPB_F5_SCALAR1 0
 #endif
@@ -493,7 +497,7 @@ struct Flood5 {
 
 template <int SS, int TR, int RPT, bool FINAL>
 // two rows per thread: 2 CTAs of 8 warps per SM (<= 128 registers); four rows: 3 CTAs of 4 warps (<= 168 registers, no spills)
-__global__ void __launch_bounds__(Cfg<SS, TR, RPT>::THREADS, RPT == 2 ? 2 : 3)
+__global__ void __launch_bounds__(Cfg<SS, TR, RPT>::THREADS, RPT == 2 ? (SS <= 8 ? VPB_F5_CTAS_R2_SMALL : 2) : 3)
 jfa_pass_flood5(const __grid_constant__ CUtensorMap tmap, const F5Args a) { Flood5<SS, TR, RPT, FINAL>::run(&tmap, a); }
 
 template <int SS, int TR, int RPT, bool FINAL>
