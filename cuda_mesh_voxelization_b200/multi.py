@@ -121,6 +121,15 @@ def parity_boundary(T: int, nxt: int, q: int) -> Tuple[Tuple[int, int], Tuple[in
     return (q, len(low)), (first_hi, len(high))
 
 
+def slab_start_buffer(total_steps: int, n_slab_steps: int) -> int:
+    """State buffer (0 / 1) the slab phase must start from after the z-cyclic phase so that the FINAL pass -- which reads one
+    buffer and leaves the other free -- frees buffer total_steps % 2: that is where the signed distance lives when it aliases a
+    state buffer (SlabPipeline.alias_sdf, grids above 1024^3), and where the ordinary path's final pass writes.  The slab
+    passes alternate start -> 1 - start -> ...; the last of the n_slab_steps passes is the final one."""
+    last_dst = total_steps % 2
+    return (1 - last_dst + n_slab_steps - 1) % 2
+
+
 def slabs_for(n: int, world: int) -> int:
     """How many z-slabs a job of side n should be cut into on `world` GPUs (last row): grids up to
     512^3 stay on ONE GPU -- a 512^3 step is ~8 ms of kernels, less than the per-pass barriers and halo copies of a
@@ -615,10 +624,7 @@ class SlabPipeline:
             self.pass_events.append((k, e0, e1))
 
     def slab_start(self, n_slab_steps):
-        """State buffer the slab phase must start from so that the FINAL pass writes into buffer len(plan.steps()) % 2 -- where
-        the signed distance lives when it aliases a state buffer (alias_sdf), and where the ordinary path's final pass writes."""
-        last_dst = len(self.plan.steps()) % 2
-        return (1 - last_dst + n_slab_steps - 1) % 2
+        return slab_start_buffer(len(self.plan.steps()), n_slab_steps)
 
     def cyclic_phase(self, targets, buf, record=False):
         """Seed extraction + every pass with k >= world in the z-cyclic layout (this rank's planes z = rank mod world as a

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cuda_mesh_voxelization_b200.multi import SlabPlan, cyclic_pieces, parity_boundary
+from cuda_mesh_voxelization_b200.multi import SlabPlan, cyclic_pieces, parity_boundary, slab_start_buffer
 
 
 def _free_port():
@@ -140,4 +140,17 @@ def test_parity_boundary_planes_cover_the_halos():
                 low |= lo_planes
                 high |= hi_planes
             assert low == set(range(nxt)) and high == set(range(T - nxt, T)), (T, nxt, low, high)
+
+
+def test_slab_phase_start_buffer_leaves_the_sdf_buffer_free():
+    """After the z-cyclic phase the slab passes ping-pong between the two extended buffers; whatever the number of GPUs, the
+    final pass must read the buffer that does NOT hold the (aliased) signed distance field, i.e. free buffer total % 2."""
+    for n in (128, 1024, 2048):
+        total = n.bit_length() - 1                       # log2(N) passes
+        for world in (2, 4, 8):
+            slab_steps = [k for k in (n >> i for i in range(1, total + 1)) if k < world]
+            cur = slab_start_buffer(total, len(slab_steps))
+            for _ in slab_steps[:-1]:
+                cur = 1 - cur                            # a pass reads cur and writes 1 - cur
+            assert 1 - cur == total % 2, (n, world)      # the final pass reads cur; the sdf may live in the other buffer
 
